@@ -1,0 +1,172 @@
+/*
+ * n2v_b200.h -- C ABI of libn2v_b200.so: the B200 (sm_100a) implementation of the
+ * node2vec-by-ecc embedding hot path
+ *
+ *     alias-table build  ->  second-order biased random walks  ->  skip-gram negative sampling
+ *     src/node2vec.py:176-204   src/node2vec.py:55-111            src/main.py:82-90 (gensim 3.2.0)
+ *
+ * (paths relative to the reference checkout). The reference is pure Python and has no FFI of
+ * its own; these entry points are what a binding for that path binds (see INTEGRATION.md for
+ * the ctypes stub that replaces src/node2vec.py and gensim.models.Word2Vec in place).
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative N2V_E* code; n2v_last_error() gives a
+ *    thread-local message. There is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with N2V_ECUDA.
+ *  - No allocation inside. Every buffer is a DEVICE pointer owned by the caller (sizes passed
+ *    explicitly); scratch space is passed in after asking the matching *_workspace_bytes().
+ *  - Asynchronous on `stream` (a cudaStream_t passed as void*), no hidden synchronisation,
+ *    current device, re-entrant across streams.
+ *  - Graphs are CSR over compact node ids 0..n-1: row_ptr int64[n+1], col int32[nnz] ascending
+ *    within each row (== the reference's sorted(G.neighbors(v)) under an order-preserving
+ *    relabel), w float64[nnz] or NULL for an unweighted graph (every weight 1).
+ *  - An alias slot is 8 bytes: { int32 alias, uint32 threshold }. With u2 = r2 * 2^-32 the
+ *    reference's test `u2 < q[kk]` (node2vec.py:278) is `r2 < ceil(q * 2^32)`; entries whose
+ *    threshold would be 2^32 store alias = own index so that either branch returns kk.
+ *  - Walk randomness: Philox4x32-10, counter (walk_id lo, walk_id hi, step, trial),
+ *    key = seed; alias mode uses words 0,1 of trial 0 as the reference's two
+ *    np.random.rand() calls of that step (u = r * 2^-32).
+ */
+#ifndef N2V_B200_H
+#define N2V_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define N2V_OK 0
+#define N2V_EINVAL (-1)   /* bad argument */
+#define N2V_ECUDA (-2)    /* CUDA runtime error (incl. no device) */
+#define N2V_ENOMEM (-3)   /* workspace too small */
+
+typedef struct { int32_t alias; uint32_t thr; } n2v_slot_t;
+
+const char *n2v_last_error(void);
+int n2v_version(void);
+/* number of SMs of the current device (grid sizing on the host side); <0 on error */
+int n2v_sm_count(void);
+
+/* ---- (1) CSR builder: networkx ingest replacement ------------------------------------
+ * replaces: nx.read_edgelist/to_undirected adjacency + sorted(G.neighbors(.)) --
+ * src/main.py:66-80, src/main_link.py:20-34, src/node2vec.py:67,184.
+ * COO arcs (src[i] -> dst[i], optional w[i]); undirected != 0 adds the reverse arcs.
+ * Duplicate arcs collapse, the LAST one in input order wins (networkx add_edge semantics).
+ * Output: row_ptr[n+1], col/w_out with capacity (undirected ? 2m : m), *nnz_out (device). */
+size_t n2v_csr_workspace_bytes(int64_t m, int32_t n_nodes, int undirected);
+int n2v_csr_from_coo(const int32_t *src, const int32_t *dst, const double *w, int64_t m,
+                     int32_t n_nodes, int undirected, void *workspace, size_t workspace_bytes,
+                     int64_t *row_ptr, int32_t *col, double *w_out, int64_t *nnz_out,
+                     void *stream);
+
+/* ---- (2) alias tables ------------------------------------------------------------------
+ * etab_ptr[e] = offset of the edge table of arc e (size deg(col[e])), etab_ptr[nnz] = total
+ * = Sigma_e deg(col[e]) (Sigma deg^2 when undirected): decides alias vs rejection mode. */
+size_t n2v_etab_workspace_bytes(int64_t nnz);
+int n2v_etab_offsets(const int64_t *row_ptr, const int32_t *col, int32_t n_nodes, int64_t nnz,
+                     int64_t *etab_ptr, void *workspace, size_t workspace_bytes, void *stream);
+
+/* replaces: per-node loop of preprocess_transition_probs (node2vec.py:184-188) and of
+ * preprocess_transition_probs_popularity (:213-218, popwalk bit 0; is_item[v] != 0 marks the
+ * '9999999'-prefixed item nodes). popwalk bit 1: the weights already are probabilities, skip
+ * the normalisation -- then each row is exactly alias_setup(probs) (node2vec.py:240-269). slots[nnz] laid out like col. Optional raw outputs
+ * J_raw int32[nnz] / q_raw float64[nnz] (the reference's (J, q)); when NULL, work_J / work_q
+ * scratch of the same sizes must be given instead. */
+int n2v_alias_build_nodes(const int64_t *row_ptr, const int32_t *col, const double *w,
+                          int32_t n_nodes, const uint8_t *is_item, int popwalk,
+                          n2v_slot_t *slots, int32_t *work_J, double *work_q, void *stream);
+
+/* replaces: get_alias_edge (node2vec.py:133-152) for every arc, i.e. the edge loop of
+ * preprocess_transition_probs (:194-199). Builds the tables of arcs [arc_begin, arc_end) into
+ * slots[etab_ptr[e] ...]; work_J/work_q hold etab_ptr[arc_end]-etab_ptr[arc_begin] entries
+ * (pass full-size arrays and keep them to read the reference's raw (J, q) back).
+ * symmetric != 0 promises an undirected (symmetric) CSR. */
+int n2v_alias_build_edges(const int64_t *row_ptr, const int32_t *col, const double *w,
+                          int32_t n_nodes, double p, double q, int symmetric,
+                          const int64_t *etab_ptr, int64_t arc_begin, int64_t arc_end,
+                          n2v_slot_t *slots, int32_t *work_J, double *work_q, void *stream);
+
+/* ---- (3) walks -------------------------------------------------------------------------
+ * replaces: simulate_walks / node2vec_walk (node2vec.py:55-95) and, same output, the
+ * on-the-fly pair (:34-53,:97-111). Walk i starts at starts[i], has global id
+ * walk_id_base + i; walks is int32[n_walks, L] padded with -1 after lens[i] (dead ends,
+ * node2vec.py:76-77). Bit-exact to the reference under injected Philox uniforms. */
+int n2v_walk_alias(const int64_t *row_ptr, const int32_t *col, const n2v_slot_t *node_slots,
+                   const int64_t *etab_ptr, const n2v_slot_t *edge_slots, const int32_t *starts,
+                   int64_t n_walks, int32_t L, uint64_t seed, uint64_t walk_id_base,
+                   int32_t *walks, int32_t *lens, void *stream);
+
+/* Rejection-sampling walker (KnightKing style) for graphs whose edge tables do not fit: same
+ * transition distribution as get_alias_edge (node2vec.py:142-150), no edge tables.
+ * node_slots may be NULL when w is NULL (uniform candidate). symmetric as above.
+ * counters: optional device uint64[4] accumulating {steps, trials, membership tests,
+ * charged probes = sum ceil(log2(deg(prev)+1))}. */
+int n2v_walk_reject(const int64_t *row_ptr, const int32_t *col, const double *w,
+                    const n2v_slot_t *node_slots, double p, double q, int symmetric,
+                    const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
+                    uint64_t walk_id_base, int32_t *walks, int32_t *lens,
+                    unsigned long long *counters, void *stream);
+
+/* ---- (4) skip-gram negative sampling -----------------------------------------------------
+ * replaces: gensim.models.Word2Vec(sentences, size, window, min_count=0, sg=1, ...) as called
+ * by learn_embeddings (src/main.py:82-90, src/main_link.py:36-41,:304-349). */
+
+/* scan_vocab: counts[id] += occurrences over tokens (negative ids = padding) */
+int n2v_vocab_count(const int32_t *tokens, int64_t n_tokens, int32_t n_ids,
+                    unsigned long long *counts, void *stream);
+
+/* scale_vocab + make_cum_table over counts in vocabulary order (count descending):
+ * keep_thr[i] = min(round(p_keep * 2^32), 2^32-1) (a token is dropped iff keep_thr < r32),
+ * cum_table[i] = round(cumsum(count^0.75)/total * (2^31-1)), and the 2^bucket_bits-entry
+ * index over the top bits of the 31-bit draw that makes bisect_left O(1) expected. */
+size_t n2v_sgns_prepare_workspace_bytes(int32_t V);
+int n2v_sgns_prepare(const unsigned long long *counts, int32_t V, double sample,
+                     uint32_t *keep_thr, uint32_t *cum_table, int32_t *bucket_lo,
+                     int32_t bucket_bits, void *workspace, size_t workspace_bytes, void *stream);
+
+/* reset_weights: syn0[i] = (u - 0.5)/dim with u from Philox keyed (seed, row, column);
+ * syn1neg = 0. */
+int n2v_sgns_init(float *syn0, float *syn1neg, int32_t V, int32_t dim, uint64_t seed,
+                  void *stream);
+
+typedef struct {
+    int32_t V;                 /* vocabulary size (rows of syn0 / syn1neg) */
+    int32_t dim;               /* multiple of 4, <= 1024 */
+    int32_t window;            /* gensim window (default 5; the reference passes 10) */
+    int32_t negative;          /* <= 16 */
+    int32_t bucket_bits;
+    int32_t max_sentence_len;  /* tokens of a sentence beyond this are ignored (<= 10000) */
+    float alpha0, min_alpha;   /* 0.025 -> 1e-4, linear in sentences dispatched */
+    int64_t total_examples;    /* corpus sentences * epochs, all ranks */
+    int64_t example_base;      /* global index of sentence 0 of this call (epoch*n + shard offset) */
+    int64_t sent_per_job;      /* alpha is constant over this many sentences (gensim: 10000-word jobs) */
+    uint32_t epoch;
+    uint64_t seed;
+    int32_t grid_warps;        /* concurrent warps (Hogwild width); 1 = sequential, deterministic */
+    int32_t atomic_updates;    /* 0 = plain stores (gensim's racy Hogwild), 1 = red.global.add */
+} n2v_sgns_params_t;
+
+/* One pass over sentences [0, n_sent): tokens int32 ids (node ids if vocab_of_id != NULL,
+ * else vocabulary indices; negative = padding), sentence s = tokens[sent_off[s] ..
+ * sent_off[s+1]) or, when sent_off == NULL, the fixed-stride row s of an [n_sent, stride]
+ * buffer (a walk buffer). sent_id_base addresses the Philox draws (global sentence id).
+ * Updates syn0/syn1neg in place; *pairs_out (device) += (centre, context) pairs trained. */
+int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                   int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                   const uint32_t *keep_thr, const uint32_t *cum_table, const int32_t *bucket_lo,
+                   const n2v_sgns_params_t *params, float *syn0, float *syn1neg,
+                   unsigned long long *pairs_out, void *stream);
+
+/* ---- measurement helpers -------------------------------------------------------------------
+ * Random-access HBM roofline denominators: mode 0 = one random 32-byte sector
+ * read per access; mode 1 = random 512-byte row read-modify-write. buf holds n_bytes;
+ * accesses per launch = n_access. sink: device uint64. */
+int n2v_random_gather_bench(void *buf, size_t n_bytes, int64_t n_access, int mode, uint64_t seed,
+                            unsigned long long *sink, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2V_B200_H */

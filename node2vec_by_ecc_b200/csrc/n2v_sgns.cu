@@ -1,0 +1,482 @@
+// Skip-gram negative sampling (north-star subsystem 4): the arithmetic of gensim 3.2.0
+// word2vec_inner.pyx train_batch_sg / fast_sentence_sg_neg, as called through
+// learn_embeddings (src/main.py:82-90).
+//
+// Work decomposition: one warp owns one sentence (walk) at a time and runs it exactly like one
+// gensim worker thread runs a sentence: sub-sample, shrink the window per position, then for
+// every (centre i, context j) pair: input row syn0[w_j], targets syn1neg[w_i] (label 1) and
+// `negative` draws from the count^0.75 table (label 0, draws equal to w_i skipped), sigmoid from
+// the 1000-entry table, immediate updates. Warps run concurrently against the same tables with
+// no locks -- gensim's Hogwild, with `grid_warps` as the Hogwild width.
+//
+// Data movement per pair (d=128, K=5): 7 rows read + 7 rows written, 512 B each = 7,168 B; each
+// lane holds one float4 of every row (16-byte vector loads, a full 512-byte row per warp
+// instruction), dots are reduced with 5 xor-shuffles. The kernel is HBM random-row bound
+// (0.64 flop/B); tensor cores do not apply.
+#include <cub/cub.cuh>
+
+#include "n2v_common.cuh"
+
+namespace n2v {
+
+constexpr int EXP_TABLE_SIZE = 1000;
+constexpr int MAX_EXP = 6;
+constexpr int SGNS_BLOCK = 128;          // 4 warps
+constexpr int SGNS_MAX_NEG = 16;
+constexpr int SGNS_SMEM_TOKENS = 256;    // per-warp staging of the kept tokens of a sentence chunk
+
+__device__ float g_exp_table[EXP_TABLE_SIZE];
+static bool g_exp_table_ready[64] = {false};
+
+// word2vec_inner.pyx init(): EXP_TABLE[i] = exp((i / 1000 * 2 - 1) * 6); x / (x + 1) -- computed
+// on the host with the same float32 casts as the Cython code, then uploaded.
+static int ensure_exp_table(cudaStream_t stream)
+{
+    int dev = 0;
+    N2V_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && g_exp_table_ready[dev]) return N2V_OK;
+    static float host_table[EXP_TABLE_SIZE];
+    for (int i = 0; i < EXP_TABLE_SIZE; ++i) {
+        float e = (float)exp(((float)i / (float)EXP_TABLE_SIZE * 2 - 1) * MAX_EXP);
+        host_table[i] = (float)(e / (e + 1));
+    }
+    N2V_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_exp_table, host_table, sizeof(host_table), 0,
+                                           cudaMemcpyHostToDevice, stream));
+    N2V_CHECK_CUDA(cudaStreamSynchronize(stream));   // host_table is static, one-time per device
+    if (dev < 64) g_exp_table_ready[dev] = true;
+    return N2V_OK;
+}
+
+// ---- vocabulary ---------------------------------------------------------------------------------
+__global__ void vocab_count_kernel(const int32_t *__restrict__ tokens, int64_t n, int32_t n_ids,
+                                   unsigned long long *__restrict__ counts)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int32_t t = tokens[i];
+        if (t >= 0 && t < n_ids) atomicAdd(counts + t, 1ull);
+    }
+}
+
+__global__ void sgns_pow_kernel(const unsigned long long *__restrict__ counts, int32_t V,
+                                double *__restrict__ powed, double *__restrict__ countd)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    double c = (double)counts[i];
+    powed[i] = pow(c, 0.75);
+    countd[i] = c;
+}
+
+__global__ void sgns_prepare_kernel(const unsigned long long *__restrict__ counts, int32_t V,
+                                    double sample, const double *__restrict__ cum_pow,
+                                    const double *__restrict__ cum_cnt,
+                                    uint32_t *__restrict__ keep_thr, uint32_t *__restrict__ cum_table)
+{
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const double retain_total = cum_cnt[V - 1], total_pow = cum_pow[V - 1];
+    double threshold;
+    if (sample <= 0.0) threshold = retain_total;
+    else if (sample < 1.0) threshold = sample * retain_total;
+    else threshold = floor(sample * (3.0 + sqrt(5.0)) / 2.0);
+    const double v = (double)counts[i];
+    double prob = (sqrt(v / threshold) + 1.0) * (threshold / v);   // scale_vocab
+    if (!(prob < 1.0)) prob = 1.0;
+    double si = round(prob * 4294967296.0);                        // sample_int
+    keep_thr[i] = si >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)si; // dropped iff sample_int < r32
+    cum_table[i] = (uint32_t)round(cum_pow[i] / total_pow * 2147483647.0);   // make_cum_table
+}
+
+// bucket_lo[b] = bisect_left(cum_table, b << shift): the search for a draw r then only spans
+// [bucket_lo[r >> shift], bucket_lo[(r >> shift) + 1]].
+__global__ void sgns_bucket_kernel(const uint32_t *__restrict__ cum_table, int32_t V,
+                                   int32_t *__restrict__ bucket_lo, int32_t bucket_bits)
+{
+    const int32_t nb = (1 << bucket_bits) + 1;
+    int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint64_t r = (uint64_t)b << (31 - bucket_bits);
+    int32_t lo = 0, hi = V;
+    while (lo < hi) { int32_t mid = (lo + hi) >> 1; if ((uint64_t)cum_table[mid] < r) lo = mid + 1; else hi = mid; }
+    bucket_lo[b] = lo;
+}
+
+__global__ void sgns_init_kernel(float *__restrict__ syn0, float *__restrict__ syn1neg, int32_t V,
+                                 int32_t dim, uint32_t k0, uint32_t k1)
+{
+    const int32_t chunks = (dim + 3) >> 2;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)V * chunks) return;
+    const int32_t row = (int32_t)(t / chunks), c = (int32_t)(t % chunks);
+    const Philox4 r = philox4x32_10((uint32_t)row, (uint32_t)c, 0x53594E30u, 0u, k0, k1);
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int32_t j = c * 4 + k;
+        if (j < dim) {
+            syn0[(int64_t)row * dim + j] = (float)(((double)rr[k] * (1.0 / 4294967296.0) - 0.5) / (double)dim);
+            if (syn1neg) syn1neg[(int64_t)row * dim + j] = 0.0f;
+        }
+    }
+}
+
+// ---- training -------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int32_t draw_negative(uint32_t r32, const uint32_t *__restrict__ cum_table,
+                                                 const int32_t *__restrict__ bucket_lo, int32_t V,
+                                                 int32_t bucket_bits)
+{
+    // bisect_left(cum_table, (next_random >> 16) % cum_table[-1])
+    const uint32_t cum_last = __ldg(cum_table + V - 1);
+    const uint32_t r = r32 % cum_last;
+    const uint32_t b = r >> (31 - bucket_bits);
+    int32_t lo = __ldg(bucket_lo + b), hi = __ldg(bucket_lo + b + 1);
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(cum_table + mid) < r) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One (centre, context) pair == one fast_sentence_sg_neg call. my_t = this lane's negative draw
+// (lane n holds negative n). Rows: row1 = syn0[context] (input), row2 = syn1neg[target].
+template <int NV, bool ATOMIC>
+__device__ __forceinline__ void apply_target(float4 *row2p, float4 (&row2)[NV], const float4 (&row1)[NV],
+                                             float4 (&work)[NV], float g, const bool (&act)[NV], int lane)
+{
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        work[c].x += g * row2[c].x; work[c].y += g * row2[c].y;       // work += g * syn1neg[t]
+        work[c].z += g * row2[c].z; work[c].w += g * row2[c].w;
+        if (act[c]) {                                                 // syn1neg[t] += g * row1
+            if (ATOMIC) {
+                atomicAdd(row2p + c * 32 + lane,
+                          make_float4(g * row1[c].x, g * row1[c].y, g * row1[c].z, g * row1[c].w));
+            } else {
+                row2[c].x += g * row1[c].x; row2[c].y += g * row1[c].y;
+                row2[c].z += g * row1[c].z; row2[c].w += g * row1[c].w;
+                row2p[c * 32 + lane] = row2[c];
+            }
+        }
+    }
+}
+
+template <int NV, bool ATOMIC>
+__device__ __forceinline__ void train_pair(float *__restrict__ syn0, float *__restrict__ syn1neg, int32_t dim,
+                                           int32_t centre, int32_t ctx, int32_t my_t, int32_t negative,
+                                           float alpha, const bool (&act)[NV], const float *s_exp, int lane)
+{
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 *row1p = reinterpret_cast<float4 *>(syn0 + (int64_t)ctx * dim);
+    float4 row1[NV], work[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) { row1[c] = act[c] ? row1p[c * 32 + lane] : zero4; work[c] = zero4; }
+
+    constexpr int FN = 5;   // fast path: gensim's default negative=5, dim <= 128
+    bool fast = (NV == 1) && (negative == FN);
+    int32_t tg[FN + 1];
+    if (fast) {
+        tg[0] = centre;
+#pragma unroll
+        for (int d = 1; d <= FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, my_t, d - 1);
+        // a repeated negative must see the row as updated by its first occurrence: slow path
+#pragma unroll
+        for (int d1 = 1; d1 <= FN; ++d1)
+#pragma unroll
+            for (int d2 = d1 + 1; d2 <= FN; ++d2) if (tg[d1] == tg[d2]) fast = false;
+    }
+    if (fast) {
+        // all target rows in flight at once: one HBM latency per pair instead of six
+        float4 r2[FN + 1][1];
+        float f[FN + 1];
+#pragma unroll
+        for (int d = 0; d <= FN; ++d) {
+            const float4 *rp = reinterpret_cast<const float4 *>(syn1neg + (int64_t)tg[d] * dim);
+            r2[d][0] = (act[0] && !(d > 0 && tg[d] == centre)) ? rp[lane] : zero4;
+        }
+#pragma unroll
+        for (int d = 0; d <= FN; ++d)
+            f[d] = row1[0].x * r2[d][0].x + row1[0].y * r2[d][0].y + row1[0].z * r2[d][0].z + row1[0].w * r2[d][0].w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int d = 0; d <= FN; ++d) f[d] += __shfl_xor_sync(0xFFFFFFFFu, f[d], o);
+#pragma unroll
+        for (int d = 0; d <= FN; ++d) {
+            if (d > 0 && tg[d] == centre) continue;                               // skipped, not redrawn
+            if (f[d] <= -(float)MAX_EXP || f[d] >= (float)MAX_EXP) continue;
+            const float sg = s_exp[(int)((f[d] + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))];
+            const float g = ((d == 0 ? 1.0f : 0.0f) - sg) * alpha;
+            float4 *row2p = reinterpret_cast<float4 *>(syn1neg + (int64_t)tg[d] * dim);
+            apply_target<1, ATOMIC>(row2p, r2[d], reinterpret_cast<const float4 (&)[1]>(row1),
+                                    reinterpret_cast<float4 (&)[1]>(work), g,
+                                    reinterpret_cast<const bool (&)[1]>(act), lane);
+        }
+    } else {
+        for (int32_t d = 0; d <= negative; ++d) {
+            int32_t target; float label;
+            if (d == 0) { target = centre; label = 1.0f; }
+            else {
+                target = __shfl_sync(0xFFFFFFFFu, my_t, d - 1);
+                if (target == centre) continue;
+                label = 0.0f;
+            }
+            float4 *row2p = reinterpret_cast<float4 *>(syn1neg + (int64_t)target * dim);
+            float4 row2[NV];
+            float f = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                row2[c] = act[c] ? row2p[c * 32 + lane] : zero4;
+                f += row1[c].x * row2[c].x + row1[c].y * row2[c].y + row1[c].z * row2[c].z + row1[c].w * row2[c].w;
+            }
+            f = warp_sum(f);
+            if (f <= -(float)MAX_EXP || f >= (float)MAX_EXP) continue;
+            const float sg = s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))];
+            const float g = (label - sg) * alpha;
+            apply_target<NV, ATOMIC>(row2p, row2, row1, work, g, act, lane);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+        if (act[c]) {                                                             // syn0[ctx] += work
+            if (ATOMIC) atomicAdd(row1p + c * 32 + lane, work[c]);
+            else {
+                row1[c].x += work[c].x; row1[c].y += work[c].y;
+                row1[c].z += work[c].z; row1[c].w += work[c].w;
+                row1p[c * 32 + lane] = row1[c];
+            }
+        }
+    }
+}
+
+struct SgnsArgs {
+    const int32_t *tokens; const int64_t *sent_off; int64_t n_sent; int32_t stride;
+    int64_t sent_id_base; const int32_t *vocab_of_id;
+    const uint32_t *keep_thr; const uint32_t *cum_table; const int32_t *bucket_lo;
+    n2v_sgns_params_t p;
+    float *syn0, *syn1neg; unsigned long long *pairs_out;
+};
+
+// NV = float4 chunks per lane (dim <= 128*NV). ATOMIC selects red.global.add.v4.f32 updates.
+template <int NV, bool ATOMIC>
+__global__ void __launch_bounds__(SGNS_BLOCK)
+sgns_train_kernel(SgnsArgs a)
+{
+    __shared__ int32_t s_idx[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ float s_exp[EXP_TABLE_SIZE];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int32_t *idx = s_idx[wib];
+    uint16_t *pos = s_pos[wib];
+    uint8_t *rw = s_rw[wib];
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = a.p.grid_warps;
+    if (warp >= n_warps) return;
+    const int32_t dim = a.p.dim, window = a.p.window, negative = a.p.negative, V = a.p.V;
+    const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
+    const uint32_t ep8 = a.p.epoch << 8;
+    bool act[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) act[c] = (c * 128 + lane * 4) < dim;
+    unsigned long long pairs = 0;
+
+    for (int64_t s = warp; s < a.n_sent; s += n_warps) {
+        const int64_t tb = a.sent_off ? a.sent_off[s] : s * (int64_t)a.stride;
+        int64_t tl = a.sent_off ? a.sent_off[s + 1] - tb : (int64_t)a.stride;
+        if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
+        const uint64_t gs = (uint64_t)(a.sent_id_base + s);
+        // job_producer: alpha fixed per job of whole sentences (word2vec.py train())
+        const int64_t ex = a.p.example_base + s;
+        const int64_t job_first = ex - ex % a.p.sent_per_job;
+        float alpha;
+        {
+            double prog = (double)job_first / (double)a.p.total_examples;
+            double al = (double)a.p.alpha0 - ((double)a.p.alpha0 - (double)a.p.min_alpha) * prog;
+            alpha = (float)(al > (double)a.p.min_alpha ? al : (double)a.p.min_alpha);
+        }
+        // --- sub-sample + window shrink, compacted in sentence order (train_batch_sg prologue).
+        // Sentences longer than the staging buffer are processed in chunks of kept tokens.
+        int64_t t_next = 0;
+        while (t_next < tl) {
+            int32_t n_kept = 0;
+            while (t_next < tl && n_kept <= SGNS_SMEM_TOKENS - 32) {
+                const int64_t t = t_next + lane;
+                int32_t wv = -1; uint32_t red = 0;
+                if (t < tl) {
+                    int32_t id = a.tokens[tb + t];
+                    if (id >= 0) wv = a.vocab_of_id ? __ldg(a.vocab_of_id + id) : id;
+                    if (wv >= 0) {
+                        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)t, ep8, k0, k1);
+                        if (a.keep_thr && __ldg(a.keep_thr + wv) < r.x) wv = -1;   // sample_int < random_int32
+                        red = r.y % (uint32_t)window;                              // reduced_windows[i]
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, wv >= 0);
+                if (wv >= 0) {
+                    const int o = n_kept + __popc(m & ((1u << lane) - 1u));
+                    idx[o] = wv; pos[o] = (uint16_t)t; rw[o] = (uint8_t)red;
+                }
+                n_kept += __popc(m);
+                t_next += 32;
+            }
+            __syncwarp();
+            // --- pairs
+            for (int32_t i = 0; i < n_kept; ++i) {
+                const int32_t centre = idx[i];
+                int32_t j = i - window + rw[i]; if (j < 0) j = 0;
+                int32_t kend = i + window + 1 - rw[i]; if (kend > n_kept) kend = n_kept;
+                for (; j < kend; ++j) {
+                    if (j == i) continue;
+                    const int32_t ctx = idx[j];
+                    // negatives: lane n draws negative n
+                    int32_t my_t = -1;
+                    if (lane < negative) {
+                        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32),
+                                                        ((uint32_t)pos[i] << 16) | (uint32_t)pos[j],
+                                                        ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
+                        const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+                        my_t = draw_negative(rr, a.cum_table, a.bucket_lo, V, a.p.bucket_bits);
+                    }
+                    train_pair<NV, ATOMIC>(a.syn0, a.syn1neg, dim, centre, ctx, my_t, negative, alpha, act, s_exp, lane);
+                    ++pairs;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && a.pairs_out && pairs) atomicAdd(a.pairs_out, pairs);
+}
+
+template <int NV>
+static int launch_train(const SgnsArgs &a, cudaStream_t stream)
+{
+    const int warps_per_block = SGNS_BLOCK / 32;
+    const int blocks = (a.p.grid_warps + warps_per_block - 1) / warps_per_block;
+    if (a.p.atomic_updates) sgns_train_kernel<NV, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+    else sgns_train_kernel<NV, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+static inline size_t align_up(size_t x, size_t al = 256) { return (x + al - 1) / al * al; }
+
+}  // namespace n2v
+
+using namespace n2v;
+
+extern "C" int n2v_vocab_count(const int32_t *tokens, int64_t n_tokens, int32_t n_ids,
+                               unsigned long long *counts, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    N2V_REQUIRE(n_tokens >= 0 && n_ids >= 0, "negative size");
+    if (n_tokens == 0) return N2V_OK;
+    N2V_REQUIRE(tokens && counts, "NULL buffer");
+    int sms = sm_count();
+    if (sms <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
+    int64_t blocks = (n_tokens + 255) / 256;
+    if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+    vocab_count_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tokens, n_tokens, n_ids, counts);
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+extern "C" size_t n2v_sgns_prepare_workspace_bytes(int32_t V)
+{
+    size_t tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, (double *)nullptr, (double *)nullptr, V);
+    return align_up(tb) + 4 * align_up(sizeof(double) * (size_t)(V > 0 ? V : 1));
+}
+
+extern "C" int n2v_sgns_prepare(const unsigned long long *counts, int32_t V, double sample,
+                                uint32_t *keep_thr, uint32_t *cum_table, int32_t *bucket_lo,
+                                int32_t bucket_bits, void *workspace, size_t workspace_bytes,
+                                void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    N2V_REQUIRE(V > 0, "empty vocabulary");
+    N2V_REQUIRE(counts && keep_thr && cum_table && bucket_lo && workspace, "NULL buffer");
+    N2V_REQUIRE(bucket_bits >= 1 && bucket_bits <= 24, "bucket_bits out of range");
+    if (n2v_sgns_prepare_workspace_bytes(V) > workspace_bytes) { set_error("sgns_prepare workspace too small"); return N2V_ENOMEM; }
+    size_t tb = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tb, (double *)nullptr, (double *)nullptr, V);
+    char *p = (char *)workspace;
+    void *cub_tmp = p; p += align_up(tb);
+    const size_t vb = align_up(sizeof(double) * (size_t)V);
+    double *powed = (double *)p; p += vb;
+    double *countd = (double *)p; p += vb;
+    double *cum_pow = (double *)p; p += vb;
+    double *cum_cnt = (double *)p;
+    const int T = 256;
+    sgns_pow_kernel<<<(V + T - 1) / T, T, 0, stream>>>(counts, V, powed, countd);
+    N2V_LAUNCH_CHECK();
+    size_t t1 = tb;
+    N2V_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, t1, powed, cum_pow, V, stream));
+    t1 = tb;
+    N2V_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, t1, countd, cum_cnt, V, stream));
+    sgns_prepare_kernel<<<(V + T - 1) / T, T, 0, stream>>>(counts, V, sample, cum_pow, cum_cnt, keep_thr, cum_table);
+    N2V_LAUNCH_CHECK();
+    const int nb = (1 << bucket_bits) + 1;
+    sgns_bucket_kernel<<<(nb + T - 1) / T, T, 0, stream>>>(cum_table, V, bucket_lo, bucket_bits);
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+extern "C" int n2v_sgns_init(float *syn0, float *syn1neg, int32_t V, int32_t dim, uint64_t seed,
+                             void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    N2V_REQUIRE(V >= 0 && dim > 0, "bad size");
+    if (V == 0) return N2V_OK;
+    N2V_REQUIRE(syn0, "syn0 is NULL");
+    const int64_t n = (int64_t)V * ((dim + 3) >> 2);
+    sgns_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(syn0, syn1neg, V, dim, (uint32_t)seed, (uint32_t)(seed >> 32));
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                              int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                              const uint32_t *keep_thr, const uint32_t *cum_table,
+                              const int32_t *bucket_lo, const n2v_sgns_params_t *params,
+                              float *syn0, float *syn1neg, unsigned long long *pairs_out,
+                              void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    N2V_REQUIRE(params, "params is NULL");
+    N2V_REQUIRE(n_sent >= 0, "negative n_sent");
+    if (n_sent == 0) return N2V_OK;
+    const n2v_sgns_params_t &p = *params;
+    N2V_REQUIRE(tokens && cum_table && bucket_lo && syn0 && syn1neg, "NULL buffer");
+    N2V_REQUIRE(sent_off || stride > 0, "need sent_off or a positive stride");
+    N2V_REQUIRE(p.V > 0 && p.dim > 0 && p.dim % 4 == 0 && p.dim <= 1024, "dim must be a multiple of 4, <= 1024");
+    N2V_REQUIRE(p.window >= 1 && p.window <= 255, "window out of range");
+    N2V_REQUIRE(p.negative >= 0 && p.negative <= SGNS_MAX_NEG, "negative out of range");
+    N2V_REQUIRE(p.max_sentence_len >= 1 && p.max_sentence_len <= 65535, "max_sentence_len out of range");
+    N2V_REQUIRE(p.grid_warps >= 1 && p.total_examples >= 1 && p.sent_per_job >= 1, "bad schedule");
+    N2V_REQUIRE(p.bucket_bits >= 1 && p.bucket_bits <= 24, "bucket_bits out of range");
+    if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
+    int rc = ensure_exp_table(stream);
+    if (rc) return rc;
+    SgnsArgs a{tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table,
+               bucket_lo, p, syn0, syn1neg, pairs_out};
+    const int nv = (p.dim + 127) / 128;
+    switch (nv) {
+        case 1: return launch_train<1>(a, stream);
+        case 2: return launch_train<2>(a, stream);
+        case 3: return launch_train<3>(a, stream);
+        case 4: return launch_train<4>(a, stream);
+        default: return launch_train<8>(a, stream);
+    }
+}

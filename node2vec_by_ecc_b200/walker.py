@@ -1,0 +1,278 @@
+"""Drop-in for the reference's ``node2vec`` module (src/node2vec.py): same class, method and
+function names, argument meaning, walk order and return shapes; the work runs in
+libn2v_b200.so on the current CUDA device. No CPU fallback.
+
+    import node2vec                      # node2vec_by_ecc_b200/dropin/node2vec.py re-exports this
+    G = node2vec.Graph(nx_G, is_directed, p, q)
+    G.preprocess_transition_probs()
+    walks = G.simulate_walks(num_walks, walk_length)
+
+Extra, optional knobs (keyword-only or environment, so existing calls stay valid):
+  seed            Philox key (default: N2V_SEED env or 0); each simulate_* call advances a walk-id
+                  base so repeated calls give fresh walks, like the reference's global numpy RNG.
+  mode            "auto" | "alias" | "reject": alias = precomputed edge tables (bit-exact to the
+                  reference under injected uniforms), reject = rejection sampling (same law, no
+                  edge tables); auto picks alias when the tables fit N2V_TABLE_BUDGET_GB.
+"""
+from __future__ import annotations
+
+import os
+from collections.abc import Sequence
+
+import numpy as np
+import torch
+
+from .graph import AliasTables, DeviceGraph
+
+
+class WalkCorpus(Sequence):
+    """The list-of-lists simulate_walks returns, kept on the device: int32[n_walks, L] compact
+    ids padded with -1. Behaves like a list of lists of ORIGINAL node labels (lazy host copy on
+    first Python access); Word2Vec consumes it without leaving the GPU."""
+
+    def __init__(self, walks: torch.Tensor, lens: torch.Tensor, labels):
+        self.walks, self.lens, self.labels = walks, lens, labels
+        self._host = None
+
+    # -- device side
+    @property
+    def walk_length(self):
+        return self.walks.shape[1]
+
+    def num_steps(self) -> int:
+        return int((self.lens.to(torch.int64) - 1).clamp_(min=0).sum().item())
+
+    def extend(self, other):
+        if not isinstance(other, WalkCorpus):
+            raise TypeError("WalkCorpus.extend needs another WalkCorpus")
+        if other.walks.shape[1] != self.walks.shape[1]:
+            raise ValueError("walk_length differs")
+        self.walks = torch.cat([self.walks, other.walks])
+        self.lens = torch.cat([self.lens, other.lens])
+        self._host = None
+
+    def __add__(self, other):
+        out = WalkCorpus(self.walks, self.lens, self.labels)
+        out.extend(other)
+        return out
+
+    # -- list-of-lists view
+    def _h(self):
+        if self._host is None:
+            self._host = (self.walks.cpu().numpy(), self.lens.cpu().numpy())
+        return self._host
+
+    def __len__(self):
+        return self.walks.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        w, l = self._h()
+        if i < 0:
+            i += len(self)
+        row = w[i, :l[i]]
+        if self.labels is None:
+            return row.tolist()
+        return self.labels[row].tolist()
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+def alias_setup(probs):
+    """node2vec.py:240-269 on the device for one distribution -> (J int64[K], q float64[K])."""
+    pr = np.asarray(probs, dtype=np.float64)
+    K = pr.shape[0]
+    if K == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float64)
+    # a star graph whose centre row carries `probs` as weights, built without normalisation
+    row_ptr = np.concatenate([[0], [K], np.full(K, K)]).astype(np.int64)
+    g = DeviceGraph.from_csr(row_ptr, np.arange(1, K + 1, dtype=np.int32), pr, symmetric=False)
+    t = g.build_node_tables(keep_raw=True, raw_probs=True)
+    return t.node_J.cpu().numpy().astype(np.int64), t.node_q.cpu().numpy()
+
+
+def alias_draw(J, q):
+    """node2vec.py:271-281 (host helper, numpy global RNG like the reference)."""
+    K = len(J)
+    kk = int(np.floor(np.random.rand() * K))
+    if np.random.rand() < q[kk]:
+        return kk
+    return J[kk]
+
+
+class _TableView:
+    """dict-like read-only view of device alias tables in the reference's (J, q) form."""
+
+    def __init__(self, graph: "Graph", edges: bool):
+        self._g, self._edges = graph, edges
+
+    def _raw(self):
+        return self._g._raw_tables()
+
+    def __getitem__(self, key):
+        dg, idx = self._g._dg, self._g._index
+        t = self._raw()
+        if not self._edges:
+            v = idx[key]
+            a, b = int(dg.row_ptr[v]), int(dg.row_ptr[v + 1])
+            return t.node_J[a:b].cpu().numpy().astype(np.int64), t.node_q[a:b].cpu().numpy()
+        u, v = idx[key[0]], idx[key[1]]
+        a, b = int(dg.row_ptr[u]), int(dg.row_ptr[u + 1])
+        pos = int(torch.searchsorted(dg.col[a:b].contiguous(), torch.tensor([v], dtype=torch.int32, device=dg.device)))
+        if pos >= b - a or int(dg.col[a + pos]) != v:
+            raise KeyError(key)
+        e = a + pos
+        o, o2 = int(t.etab_ptr[e]), int(t.etab_ptr[e + 1])
+        return t.edge_J[o:o2].cpu().numpy().astype(np.int64), t.edge_q[o:o2].cpu().numpy()
+
+    def __len__(self):
+        return self._g._dg.nnz if self._edges else self._g._dg.n
+
+
+class Graph:
+    """Same constructor and methods as the reference class (node2vec.py:5-237)."""
+
+    def __init__(self, nx_G, is_directed, p, q, popwalk="none", *, seed=None, mode="auto"):
+        self.G = nx_G
+        self.is_directed = is_directed
+        self.p = p
+        self.q = q
+        self.popwalk = popwalk
+        self.seed = int(os.environ.get("N2V_SEED", "0")) if seed is None else int(seed)
+        self.mode = os.environ.get("N2V_WALK_MODE", mode)
+        self._reset()
+
+    def _reset(self):
+        self._dg_obj = None
+        self._dg_for = None
+        self._tables = None
+        self._tables_raw = None
+        self._walk_id_base = 0
+
+    # Graph instances are pickled to pool workers by main_link.py:277; device handles stay behind.
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_dg_obj", "_dg_for", "_tables", "_tables_raw"):
+            st[k] = None
+        return st
+
+    # ---- device graph, rebuilt when the caller swaps/mutates self.G (main_link.py:592) ----------
+    @property
+    def _dg(self) -> DeviceGraph:
+        key = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
+        if self._dg_obj is None or self._dg_for != key:
+            self._dg_obj = DeviceGraph.from_networkx(self.G)
+            self._dg_for = key
+            self._tables = self._tables_raw = None
+            self._index_map = {l: i for i, l in enumerate(self._dg_obj.labels.tolist())}
+        return self._dg_obj
+
+    @property
+    def _index(self):
+        self._dg
+        return self._index_map
+
+    def _table_budget(self) -> int:
+        gb = float(os.environ.get("N2V_TABLE_BUDGET_GB", "0"))
+        if gb > 0:
+            return int(gb * 2 ** 30)
+        free, _ = torch.cuda.mem_get_info()
+        return int(free * 0.4)
+
+    def _use_alias(self) -> bool:
+        if self.mode == "alias":
+            return True
+        if self.mode == "reject":
+            return False
+        return self._dg.edge_table_bytes() * 2.5 <= self._table_budget()   # slots + build scratch
+
+    def _build(self, popwalk_nodes: bool, edges: bool, keep_raw=False) -> AliasTables:
+        dg = self._dg
+        if edges:
+            return dg.build_alias_tables(float(self.p), float(self.q), popwalk=popwalk_nodes, keep_raw=keep_raw)
+        return dg.build_node_tables(popwalk=popwalk_nodes, keep_raw=keep_raw)
+
+    def _raw_tables(self) -> AliasTables:
+        if self._tables_raw is None:
+            pop = bool(self._tables.popwalk) if self._tables is not None else False
+            self._tables_raw = self._build(pop, edges=True, keep_raw=True)
+        return self._tables_raw
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def preprocess_transition_probs(self):
+        """node2vec.py:176-204. Node tables always; edge tables when they fit (else the walks use
+        the rejection sampler, which needs none)."""
+        self._tables = self._build(False, edges=self._use_alias())
+        self._tables_raw = None
+        self.alias_nodes = _TableView(self, edges=False)
+        self.alias_edges = _TableView(self, edges=True)
+        return
+
+    def preprocess_transition_probs_popularity(self):
+        """node2vec.py:206-237: popularity-normalised node tables, plain edge tables (:228-232)."""
+        self._tables = self._build(True, edges=self._use_alias())
+        self._tables_raw = None
+        self.alias_nodes = _TableView(self, edges=False)
+        self.alias_edges = _TableView(self, edges=True)
+        return
+
+    def _starts(self, num_walks, nodes):
+        dg = self._dg
+        if not nodes:                                   # `if not nodes` (node2vec.py:87)
+            order = dg.order
+        else:
+            idx = self._index
+            order = torch.as_tensor(np.fromiter((idx[x] for x in nodes), dtype=np.int32, count=len(nodes)),
+                                    device=dg.device)
+        return order.repeat(int(num_walks))             # walk_iter-major, then nodes (:89-93)
+
+    def _simulate(self, num_walks, walk_length, nodes, tables: AliasTables, verbose):
+        dg = self._dg
+        starts = self._starts(num_walks, nodes)
+        if verbose:
+            for it in range(int(num_walks)):
+                print(str(it + 1), '/', str(num_walks))
+        base = self._walk_id_base
+        self._walk_id_base += int(starts.shape[0])
+        if tables.edge_slots is not None:
+            walks, lens = dg.walk_alias(tables, starts, int(walk_length), self.seed, base)
+        else:
+            walks, lens = dg.walk_reject(float(self.p), float(self.q), starts, int(walk_length), self.seed,
+                                         base, node_tables=tables)
+        return WalkCorpus(walks, lens, dg.labels)
+
+    def simulate_walks(self, num_walks, walk_length, nodes=None, verbose=False):
+        """node2vec.py:81-95."""
+        if getattr(self, "_tables", None) is None:
+            raise AttributeError("'Graph' object has no attribute 'alias_nodes' "
+                                 "(call preprocess_transition_probs() first)")
+        return self._simulate(num_walks, walk_length, nodes, self._tables, verbose)
+
+    def simulate_walks_on_the_fly(self, num_walks, walk_length, nodes=None, verbose=False):
+        """node2vec.py:97-111: same walks without a prior preprocess call. popwalk "pop" follows
+        get_alias_nodes_cur / get_alias_edge_pop (:13-32,:154-174), whose edge law ignores q."""
+        if self.popwalk == "pop":
+            raise NotImplementedError("popwalk='pop' on-the-fly walks (get_alias_edge_pop) are not built yet")
+        key = ("otf", float(self.p), float(self.q))
+        if self._tables is None or getattr(self, "_otf_key", None) != key or self._tables.popwalk:
+            self._dg
+            self._tables = self._build(False, edges=self._use_alias())
+            self._tables_raw = None
+            self._otf_key = key
+        return self._simulate(num_walks, walk_length, nodes, self._tables, verbose)
+
+    def node2vec_walk(self, walk_length, start_node):
+        """node2vec.py:55-79: one walk (one launch; use simulate_walks for throughput)."""
+        return self.simulate_walks(1, walk_length, nodes=[start_node])[0]
+
+    def node2vec_walk_on_the_fly(self, walk_length, start_node):
+        return self.simulate_walks_on_the_fly(1, walk_length, nodes=[start_node])[0]
+
+    def get_alias_edge(self, src, dst):
+        """node2vec.py:133-152 -> (J, q) of one arc."""
+        if self._tables is None:
+            self._tables = self._build(False, edges=True)
+        return _TableView(self, edges=True)[(src, dst)]

@@ -1,0 +1,285 @@
+"""Drop-in for the gensim 3.2.0 surface the reference uses (src/main.py:82-90,
+src/main_link.py:36-41,:304-349,:43-61,:127-131,:173-189): ``Word2Vec(sentences, size=, window=,
+min_count=, sg=1, workers=, iter=)`` -> model with ``.wv`` (KeyedVectors-compatible), and
+``LineSentence``. Training runs in libn2v_b200.so (n2v_sgns_train); there is no CPU fallback.
+
+Only what gensim does for ``sg=1, hs=0, negative>0`` is implemented; other modes raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from ._lib import SgnsParams, check, lib, ptr, require_cuda, stream
+from .walker import WalkCorpus
+
+
+class Vocab:
+    """gensim.models.keyedvectors.Vocab: .index, .count, .sample_int"""
+    __slots__ = ("index", "count", "sample_int")
+
+    def __init__(self, index, count, sample_int=None):
+        self.index, self.count, self.sample_int = index, count, sample_int
+
+    def __repr__(self):
+        return f"Vocab(count:{self.count}, index:{self.index})"
+
+
+class LineSentence:
+    """gensim.models.word2vec.LineSentence: one sentence per line, whitespace separated
+    (the walk files of main_link.py:237-239,544-546), at most max_sentence_length words each."""
+
+    def __init__(self, source, max_sentence_length=10000, limit=None):
+        self.source, self.max_sentence_length, self.limit = source, max_sentence_length, limit
+
+    def __iter__(self):
+        close = False
+        f = self.source
+        if isinstance(f, (str, os.PathLike)):
+            f = open(f, "r")
+            close = True
+        try:
+            if hasattr(f, "seek"):
+                f.seek(0)
+            for n, line in enumerate(f):
+                if self.limit is not None and n >= self.limit:
+                    break
+                if isinstance(line, bytes):
+                    line = line.decode("utf8")
+                words = line.split()
+                for i in range(0, len(words), self.max_sentence_length):
+                    yield words[i:i + self.max_sentence_length]
+        finally:
+            if close:
+                f.close()
+
+
+class KeyedVectors:
+    """The part of gensim.models.KeyedVectors the reference touches."""
+
+    def __init__(self, vector_size=0):
+        self.vocab = {}
+        self.index2word = []
+        self.vector_size = vector_size
+        self._syn0_dev = None
+        self._syn0_host = None
+
+    @property
+    def syn0(self):
+        """float32[V, d] numpy, copied from the device lazily"""
+        if self._syn0_host is None and self._syn0_dev is not None:
+            self._syn0_host = self._syn0_dev.cpu().numpy()
+        return self._syn0_host
+
+    @syn0.setter
+    def syn0(self, v):
+        self._syn0_host = np.asarray(v, dtype=np.float32)
+        self._syn0_dev = None
+
+    vectors = syn0
+
+    def __contains__(self, word):
+        return word in self.vocab
+
+    def word_vec(self, word):
+        if word not in self.vocab:
+            raise KeyError("word '%s' not in vocabulary" % word)
+        return self.syn0[self.vocab[word].index]
+
+    def __getitem__(self, words):
+        if isinstance(words, (str, bytes)):
+            return self.word_vec(words)
+        return np.vstack([self.word_vec(w) for w in words])
+
+    def similarity(self, w1, w2):
+        """cosine of the two rows (link_score 'cos', main_link.py:43-49)"""
+        a, b = self.word_vec(w1), self.word_vec(w2)
+        return float(np.dot(a / np.linalg.norm(a), b / np.linalg.norm(b)))
+
+    def most_similar(self, positive, topn=10):
+        if isinstance(positive, (str, bytes)):
+            positive = [positive]
+        m = self.syn0 / np.linalg.norm(self.syn0, axis=1, keepdims=True)
+        v = np.mean([m[self.vocab[w].index] for w in positive], axis=0)
+        d = m @ (v / np.linalg.norm(v))
+        skip = {self.vocab[w].index for w in positive}
+        out = [(self.index2word[i], float(d[i])) for i in np.argsort(-d) if i not in skip]
+        return out[:topn]
+
+    def save_word2vec_format(self, fname, fvocab=None, binary=False, total_vec=None):
+        """text format read back by utils.emb_file_to_user_dict (utils.py:417-426):
+        'V d' then 'word v1 ... vd', vocabulary (count-descending) order."""
+        if binary:
+            raise NotImplementedError("binary word2vec format is not needed by the reference")
+        syn0 = self.syn0
+        with open(fname, "w") as f:
+            f.write("%d %d\n" % (len(self.index2word), self.vector_size))
+            for i, word in enumerate(self.index2word):
+                f.write("%s %s\n" % (word, " ".join("%f" % v for v in syn0[i])))
+
+
+class Word2Vec:
+    """gensim.models.Word2Vec(sg=1, hs=0, negative=k) on the GPU. Signature and defaults are
+    gensim 3.2.0's; the reference passes size, window, min_count=0, sg=1, workers, iter."""
+
+    def __init__(self, sentences=None, size=100, alpha=0.025, window=5, min_count=5,
+                 max_vocab_size=None, sample=1e-3, seed=1, workers=3, min_alpha=0.0001,
+                 sg=0, hs=0, negative=5, cbow_mean=1, hashfxn=hash, iter=5, null_word=0,
+                 trim_rule=None, sorted_vocab=1, batch_words=10000, compute_loss=False,
+                 *, hogwild_warps=None, atomic_updates=None):
+        if not sg or hs or negative <= 0:
+            raise NotImplementedError("only skip-gram with negative sampling (sg=1, hs=0, negative>0) "
+                                      "is implemented: it is the only mode the reference uses")
+        self.vector_size = self.layer1_size = int(size)
+        self.alpha, self.min_alpha = float(alpha), float(min_alpha)
+        self.window, self.min_count, self.sample = int(window), int(min_count), float(sample)
+        self.seed, self.workers, self.negative = int(seed), int(workers), int(negative)
+        self.iter, self.batch_words = int(iter), int(batch_words)
+        self.sg, self.hs = 1, 0
+        self.hogwild_warps = hogwild_warps
+        self.atomic_updates = (int(os.environ.get("N2V_SGNS_ATOMIC", "0")) if atomic_updates is None
+                               else int(atomic_updates))
+        self.wv = KeyedVectors(self.vector_size)
+        self.corpus_count = 0
+        self.train_count = 0
+        self.pairs_trained = 0
+        self.syn1neg = None
+        if sentences is not None:
+            self.build_vocab(sentences)
+            self.train(self._corpus, total_examples=self.corpus_count, epochs=self.iter)
+
+    # gensim forwards these to .wv
+    def __getitem__(self, w):
+        return self.wv[w]
+
+    def __contains__(self, w):
+        return w in self.wv
+
+    def similarity(self, a, b):
+        return self.wv.similarity(a, b)
+
+    # ---- corpus ingest -----------------------------------------------------------------------
+    def _ingest(self, sentences):
+        """-> (tokens int32 device [n_tok] or [n_sent, stride], sent_off device|None, stride,
+        n_sent, words list indexed by token id)"""
+        dev = require_cuda()
+        if isinstance(sentences, WalkCorpus):     # already on the device: tokens are compact node ids
+            labels = sentences.labels
+            n_ids = int(len(labels)) if labels is not None else int(sentences.walks.max().item()) + 1
+            words = [str(l) for l in (labels.tolist() if labels is not None else range(n_ids))]
+            return sentences.walks, None, int(sentences.walks.shape[1]), int(sentences.walks.shape[0]), words
+        # generic iterable of iterables of tokens (materialised once: py3 `map` objects are one-shot,
+        # gensim needs >= 2 passes -- SURVEY.md section 2)
+        ids = {}
+        toks, offs = [], [0]
+        for sent in sentences:
+            for wd in sent:
+                i = ids.get(wd)
+                if i is None:
+                    i = ids[wd] = len(ids)
+                toks.append(i)
+            offs.append(len(toks))
+        words = [None] * len(ids)
+        for wd, i in ids.items():
+            words[i] = wd
+        tok = torch.as_tensor(np.asarray(toks, dtype=np.int32)).to(dev)
+        off = torch.as_tensor(np.asarray(offs, dtype=np.int64)).to(dev)
+        return tok, off, 0, len(offs) - 1, words
+
+    def build_vocab(self, sentences, **_):
+        """scan_vocab + scale_vocab + finalize_vocab (word2vec.py): count, drop < min_count, sort by
+        count descending (ties: first seen), sub-sampling thresholds, cum_table, reset_weights."""
+        dev = require_cuda()
+        L = lib()
+        tok, off, stride, n_sent, words = self._ingest(sentences)
+        self._corpus = (tok, off, stride, n_sent)
+        self.corpus_count = n_sent
+        n_ids = len(words)
+        counts = torch.zeros(max(n_ids, 1), dtype=torch.int64, device=dev)
+        check(L.n2v_vocab_count(ptr(tok), C.c_int64(tok.numel()), C.c_int32(n_ids), ptr(counts), stream()))
+        counts = counts[:n_ids]
+        keep = counts >= max(self.min_count, 1)
+        # count descending, ties by id: ids are first-seen order for generic corpora and compact node
+        # ids for walk corpora (gensim's tie order is dict order -- unspecified in Python 2)
+        order = torch.sort(torch.where(keep, counts, torch.zeros_like(counts)), descending=True, stable=True).indices
+        V = int(keep.sum().item())
+        if V == 0:
+            raise RuntimeError("you must first build vocabulary before training the model")
+        order = order[:V].contiguous()
+        vcounts = counts[order].contiguous()
+        vocab_of_id = torch.full((n_ids,), -1, dtype=torch.int32, device=dev)
+        vocab_of_id[order] = torch.arange(V, dtype=torch.int32, device=dev)
+        self._vocab_of_id = vocab_of_id
+        self._bucket_bits = int(min(20, max(4, int(np.ceil(np.log2(V))) + 2)))
+        self._keep_thr = torch.empty(V, dtype=torch.int32, device=dev)
+        self._cum_table = torch.empty(V, dtype=torch.int32, device=dev)
+        self._bucket_lo = torch.empty((1 << self._bucket_bits) + 1, dtype=torch.int32, device=dev)
+        ws_bytes = int(L.n2v_sgns_prepare_workspace_bytes(C.c_int32(V)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.n2v_sgns_prepare(ptr(vcounts), C.c_int32(V), C.c_double(self.sample), ptr(self._keep_thr),
+                                 ptr(self._cum_table), ptr(self._bucket_lo), C.c_int32(self._bucket_bits),
+                                 ptr(ws), C.c_size_t(ws_bytes), stream()))
+        self._raw_words = int(counts.sum().item())
+        # host-side vocabulary objects (what emb.vocab / index2word expose)
+        order_h, vc_h = order.cpu().numpy(), vcounts.cpu().numpy()
+        kt_h = self._keep_thr.cpu().numpy().view(np.uint32)
+        self.wv.index2word = [words[i] for i in order_h]
+        self.wv.vocab = {w: Vocab(i, int(vc_h[i]), int(kt_h[i])) for i, w in enumerate(self.wv.index2word)}
+        self.wv.vector_size = self.vector_size
+        self.reset_weights()
+
+    def reset_weights(self):
+        dev = require_cuda()
+        V, d = len(self.wv.index2word), self.vector_size
+        self._syn0 = torch.empty((V, d), dtype=torch.float32, device=dev)
+        self.syn1neg_dev = torch.empty((V, d), dtype=torch.float32, device=dev)
+        check(lib().n2v_sgns_init(ptr(self._syn0), ptr(self.syn1neg_dev), C.c_int32(V), C.c_int32(d),
+                                  C.c_uint64(self.seed), stream()))
+        self.wv._syn0_dev, self.wv._syn0_host = self._syn0, None
+
+    # ---- training ------------------------------------------------------------------------------
+    def default_hogwild_warps(self, V: int) -> int:
+        """Concurrent sentences. gensim runs `workers` (8-12) sentences at a time against the shared
+        tables; the GPU runs thousands. Collisions on the same rows scale with width/V, so the width
+        is capped at V/8 rows-per-warp for small vocabularies and at the machine width otherwise."""
+        sms = int(lib().n2v_sm_count())
+        full = sms * 16
+        return int(max(4, min(full, V // 8)))
+
+    def train(self, sentences=None, total_examples=None, total_words=None, epochs=None,
+              start_alpha=None, end_alpha=None, **_):
+        if sentences is None or isinstance(sentences, tuple):
+            tok, off, stride, n_sent = self._corpus if sentences is None else sentences
+        else:
+            raise NotImplementedError("train() on a new corpus: rebuild the model with that corpus")
+        epochs = self.iter if epochs is None else int(epochs)
+        alpha0 = self.alpha if start_alpha is None else float(start_alpha)
+        min_alpha = self.min_alpha if end_alpha is None else float(end_alpha)
+        V = len(self.wv.index2word)
+        dev = self._syn0.device
+        pairs = torch.zeros(1, dtype=torch.int64, device=dev)
+        mean_len = max(1.0, self._raw_words / max(n_sent, 1))
+        P = SgnsParams()
+        P.V, P.dim, P.window, P.negative = V, self.vector_size, self.window, self.negative
+        P.bucket_bits, P.max_sentence_len = self._bucket_bits, 10000
+        P.alpha0, P.min_alpha = alpha0, min_alpha
+        P.total_examples = int(n_sent) * epochs
+        P.sent_per_job = max(1, int(self.batch_words // mean_len))
+        P.seed = self.seed
+        P.grid_warps = int(self.hogwild_warps or self.default_hogwild_warps(V))
+        P.atomic_updates = int(self.atomic_updates)
+        for ep in range(epochs):
+            P.epoch = ep
+            P.example_base = ep * int(n_sent)
+            check(lib().n2v_sgns_train(ptr(tok), ptr(off), C.c_int64(n_sent), C.c_int32(stride), C.c_int64(0),
+                                       ptr(self._vocab_of_id), ptr(self._keep_thr if self.sample > 0 else None),
+                                       ptr(self._cum_table), ptr(self._bucket_lo), C.byref(P), ptr(self._syn0),
+                                       ptr(self.syn1neg_dev), ptr(pairs), stream()))
+        self.pairs_trained += int(pairs.item())
+        self.train_count += 1
+        self.wv._syn0_dev, self.wv._syn0_host = self._syn0, None
+        self.syn1neg = None
+        return self.pairs_trained

@@ -1,0 +1,135 @@
+"""GPU: walks through the C ABI. Alias mode is bit-exact against (a) walks the reference itself
+produced with Philox uniforms injected into np.random.rand (tests/golden) and (b) the C oracle on
+larger seeded graphs; rejection mode passes chi-square against the exact transition rows."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import CASES, chi_square_p, load_case, random_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_graph(g, symmetric, is_item=None):
+    from node2vec_by_ecc_b200 import DeviceGraph
+    return DeviceGraph.from_csr(g.row_ptr, g.col, g.w, symmetric=symmetric, is_item=is_item)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_walks_bit_exact_vs_reference_golden(name):
+    z, g = load_case(name)
+    L, seed = int(z["L"]), int(z["seed"])
+    dg = dev_graph(g, symmetric=not bool(int(z["directed"])), is_item=z["is_item"])
+    t = dg.build_alias_tables(float(z["p"]), float(z["q"]), popwalk=bool(int(z["popwalk"])))
+    starts = torch.as_tensor(np.tile(z["order"], int(z["R"])))
+    walks, lens = dg.walk_alias(t, starts, L, seed)
+    assert (lens.cpu().numpy() == z["lens"]).all()
+    assert (walks.cpu().numpy() == z["walks"]).all()
+    # a contiguous shard of start nodes with a walk-id base (main_link.py:263-264 partitioning)
+    sub = torch.as_tensor(np.tile(z["sub_starts"], 2))
+    walks, lens = dg.walk_alias(t, sub, L, seed, walk_id_base=1000)
+    assert (walks.cpu().numpy() == z["walks_sub"]).all() and (lens.cpu().numpy() == z["lens_sub"]).all()
+
+
+@pytest.mark.parametrize("weighted,directed,p,q,L", [(False, False, 0.25, 4.0, 80), (True, False, 0.5, 2.0, 40),
+                                                      (True, True, 4.0, 0.25, 33), (False, True, 1.0, 1.0, 7)])
+def test_walks_bit_exact_vs_oracle(weighted, directed, p, q, L):
+    _, g = random_graph(2000, 30000, seed=21, weighted=weighted, directed=directed, skew=1.0)
+    to = oracle.preprocess(g, p, q)
+    starts = np.tile(np.arange(g.n, dtype=np.int32), 3)
+    want, want_len = oracle.walks_alias(g, to, starts, L, seed=77, walk_id_base=5)
+    dg = dev_graph(g, symmetric=not directed)
+    t = dg.build_alias_tables(p, q)
+    walks, lens = dg.walk_alias(t, torch.as_tensor(starts), L, seed=77, walk_id_base=5)
+    assert (lens.cpu().numpy() == want_len).all()
+    assert (walks.cpu().numpy() == want).all()
+    if directed:
+        assert (want_len < L).any()          # dead ends exercised
+
+
+def test_sharding_is_invisible():
+    """walk ids are global: any split of the start list gives the same corpus (multi-GPU rule)."""
+    _, g = random_graph(3000, 40000, seed=8, skew=0.7)
+    dg = dev_graph(g, symmetric=True)
+    t = dg.build_alias_tables(0.25, 4.0)
+    starts = torch.arange(g.n, dtype=torch.int32).repeat(2)
+    full, _ = dg.walk_alias(t, starts, 40, seed=3)
+    cuts = [0, 1111, 2500, 4096, starts.shape[0]]
+    parts = [dg.walk_alias(t, starts[a:b], 40, seed=3, walk_id_base=a)[0] for a, b in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(full, torch.cat(parts))
+
+
+def transition_counts(walks, lens, n):
+    w = walks.cpu().numpy()
+    ok = lens.cpu().numpy() >= 3
+    w = w[ok]
+    key = (w[:, 0].astype(np.int64) * n + w[:, 1]) * n + w[:, 2]
+    u, c = np.unique(key, return_counts=True)
+    return u, c
+
+
+@pytest.mark.parametrize("weighted,directed,p,q", [(False, False, 0.25, 4.0), (False, False, 4.0, 0.25),
+                                                    (False, False, 1.0, 1.0), (True, False, 0.25, 4.0),
+                                                    (True, True, 0.5, 2.0), (False, True, 4.0, 0.5)])
+def test_rejection_walker_chi_square(weighted, directed, p, q):
+    n = 300
+    _, g = random_graph(n, 3000, seed=31, weighted=weighted, directed=directed, skew=1.0)
+    dg = dev_graph(g, symmetric=not directed)
+    deg = np.diff(g.row_ptr)
+    hub = int(np.argmax(deg))
+    # walks of 3 tokens: (start=a) -> b -> c ; c | (a, b) must follow get_alias_edge(a, b)
+    starts_np = np.concatenate([np.full(400000, hub, dtype=np.int32),
+                                np.repeat(np.arange(n, dtype=np.int32), 2000)])
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    walks, lens = dg.walk_reject(p, q, torch.as_tensor(starts_np), 3, seed=99, counters=counters)
+    cnt = counters.cpu().numpy()
+    assert cnt[0] == int((lens.cpu().numpy() - 1).sum()) and cnt[1] >= cnt[0]
+    keys, c = transition_counts(walks, lens, n)
+    a, b, nxt = keys // (n * n), (keys // n) % n, keys % n
+    pair = a * n + b
+    upair, tot = np.unique(pair, return_counts=False), None
+    sums = {}
+    for pk, cc in zip(pair, c):
+        sums[pk] = sums.get(pk, 0) + cc
+    tested, pvals = 0, []
+    for pk in sorted(sums, key=lambda k: -sums[k])[:60]:
+        aa, bb = int(pk // n), int(pk % n)
+        probs = oracle.transition_row(g, p, q, aa, bb)
+        row = g.col[g.row_ptr[bb]:g.row_ptr[bb + 1]]
+        obs = np.zeros(len(row))
+        sel = pair == pk
+        pos = np.searchsorted(row, nxt[sel])
+        assert (row[pos] == nxt[sel]).all()          # only real neighbours are ever produced
+        obs[pos] = c[sel]
+        pvals.append(chi_square_p(obs, probs))
+        tested += 1
+    assert tested >= 30
+    pvals = np.asarray(pvals)
+    # 60 independent tests: no catastrophic cell, and the p-values are not piled up near 0
+    assert pvals.min() > 1e-5, pvals.min()
+    assert (pvals < 0.01).sum() <= 4, np.sort(pvals)[:6]
+
+
+def test_rejection_first_step_follows_node_table():
+    _, g = random_graph(200, 2500, seed=4, weighted=True, skew=0.5)
+    dg = dev_graph(g, symmetric=True)
+    v = int(np.argmax(np.diff(g.row_ptr)))
+    walks, lens = dg.walk_reject(0.25, 4.0, torch.full((300000,), v, dtype=torch.int32), 2, seed=5)
+    row = g.col[g.row_ptr[v]:g.row_ptr[v + 1]]
+    probs = oracle.transition_row(g, 1.0, 1.0, -1, v)
+    obs = np.bincount(np.searchsorted(row, walks.cpu().numpy()[:, 1]), minlength=len(row))
+    assert chi_square_p(obs, probs) > 1e-4
+
+
+def test_alias_and_rejection_agree_on_visit_frequencies():
+    _, g = random_graph(1000, 15000, seed=13, skew=1.0)
+    dg = dev_graph(g, symmetric=True)
+    t = dg.build_alias_tables(0.25, 4.0)
+    starts = torch.arange(g.n, dtype=torch.int32).repeat(20)
+    wa, _ = dg.walk_alias(t, starts, 40, seed=1)
+    wr, _ = dg.walk_reject(0.25, 4.0, starts, 40, seed=2)
+    fa = np.bincount(wa.cpu().numpy().ravel(), minlength=g.n).astype(np.float64)
+    fr = np.bincount(wr.cpu().numpy().ravel(), minlength=g.n).astype(np.float64)
+    fa, fr = fa / fa.sum(), fr / fr.sum()
+    assert np.abs(fa - fr).sum() < 0.03       # total-variation-ish distance between visit laws
