@@ -66,11 +66,20 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_dummy = {}
+
+
 def ptr(t):
-    """device pointer of a tensor (None -> NULL)"""
+    """device pointer of a tensor (None -> NULL). Empty tensors get a valid dummy address: the C
+    ABI treats NULL as "absent", zero sizes are passed explicitly."""
     if t is None:
         return C.c_void_p(0)
     assert t.is_cuda and t.is_contiguous(), "need a contiguous CUDA tensor"
+    if t.numel() == 0:
+        d = _dummy.get(t.device)
+        if d is None:
+            d = _dummy[t.device] = torch.zeros(64, dtype=torch.uint8, device=t.device)
+        return C.c_void_p(d.data_ptr())
     return C.c_void_p(t.data_ptr())
 
 

@@ -28,8 +28,8 @@ __device__ __forceinline__ void flush_stage(int32_t (*stage)[STAGE + 1], int32_t
     __syncwarp();
     const int c = lane & 7;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int wl = (lane >> 3) + 8 * r;            // walker within the warp
+    for (int r = 0; r < 8; ++r) {
+        const int wl = (lane >> 3) + 4 * r;            // walker within the warp (4 sectors per pass)
         const int64_t wi = w0 + wl;
         const int32_t s = s0 + c;
         if (wi < n_walks && s < L) walks[wi * L + s] = stage[wl][c];
@@ -125,16 +125,16 @@ walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
             else {
                 int32_t nxt = -1;
                 uint32_t trial = 0;
-                if (prev >= 0 && rp.fold) {
-                    // outlier: the return edge carries (1/p - B') extra mass on top of the B'
-                    // dartboard of area B'*K (unit weights): take it with that share.
-                    const Philox4 r = philox4x32_10((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)s, 0xFFFFFFFFu, k0, k1);
-                    const double u = ((double)r.x + (double)r.y * (1.0 / 4294967296.0)) * (1.0 / 4294967296.0);
-                    if (u * (rp.bound * (double)K + rp.fold_mass) < rp.fold_mass) nxt = prev;
-                }
                 while (nxt < 0) {
                     const Philox4 r = philox4x32_10((uint32_t)wid, (uint32_t)(wid >> 32), (uint32_t)s, trial, k0, k1);
                     ++trial;
+                    if (rp.fold && prev >= 0) {
+                        // outlier: the return edge carries (1/p - B') extra area on top of the
+                        // B'-high dartboard of K unit-weight columns; a dart lands there with
+                        // that share of the total area and is always accepted (re-drawn per trial).
+                        const double u = (double)r.w * (1.0 / 4294967296.0);
+                        if (u * (rp.bound * (double)K + rp.fold_mass) < rp.fold_mass) { nxt = prev; break; }
+                    }
                     int64_t k = (int64_t)__umul64hi((uint64_t)r.x << 32, (uint64_t)K);   // floor(u*K)
                     if (WEIGHTED) {   // static law ~ w(cur, .): the node alias table
                         const uint2 sl = __ldg(reinterpret_cast<const uint2 *>(node_slots + b + k));

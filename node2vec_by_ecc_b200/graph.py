@@ -78,9 +78,10 @@ class DeviceGraph:
                                  C.c_int(int(undirected)), ptr(ws), C.c_size_t(ws_bytes), ptr(row_ptr),
                                  ptr(col), ptr(w_out), ptr(nnz_d), stream()))
         nnz = int(nnz_d.item())
-        col = col[:nnz].clone() if nnz < cap else col
+        # (a zero-length view keeps a non-NULL data pointer for the C ABI)
+        col = col[:nnz].clone() if 0 < nnz < cap else col[:nnz]
         if w_out is not None:
-            w_out = w_out[:nnz].clone() if nnz < cap else w_out
+            w_out = w_out[:nnz].clone() if 0 < nnz < cap else w_out[:nnz]
         if order is not None:
             order = torch.as_tensor(order, dtype=torch.int32).to(dev).contiguous()
         if is_item is not None:

@@ -121,6 +121,80 @@ class KeyedVectors:
                 f.write("%s %s\n" % (word, " ".join("%f" % v for v in syn0[i])))
 
 
+class SgnsTrainer:
+    """Device state of one SGNS job -- vocabulary tables (scale_vocab / make_cum_table), syn0 and
+    syn1neg -- and the launcher of n2v_sgns_train. Word2Vec below is the gensim-shaped front;
+    bench.py drives this class directly on device-resident walk buffers."""
+
+    def __init__(self, counts_by_id: torch.Tensor, dim=128, window=10, negative=5, sample=1e-3, seed=1,
+                 alpha=0.025, min_alpha=1e-4, min_count=0, batch_words=10000):
+        dev = require_cuda()
+        L = lib()
+        counts = counts_by_id.to(device=dev, dtype=torch.int64).contiguous()
+        n_ids = int(counts.shape[0])
+        self.dim, self.window, self.negative, self.sample = int(dim), int(window), int(negative), float(sample)
+        self.seed, self.alpha, self.min_alpha, self.batch_words = int(seed), float(alpha), float(min_alpha), int(batch_words)
+        keep = counts >= max(int(min_count), 1)
+        # count descending, ties by id: ids are first-seen order for generic corpora and compact node
+        # ids for walk corpora (gensim's tie order is dict order -- unspecified in Python 2)
+        order = torch.sort(torch.where(keep, counts, torch.zeros_like(counts)), descending=True, stable=True).indices
+        V = int(keep.sum().item())
+        if V == 0:
+            raise RuntimeError("you must first build vocabulary before training the model")
+        self.V = V
+        self.order = order[:V].contiguous()                       # vocabulary index -> token id
+        self.counts = counts[self.order].contiguous()
+        self.raw_words = int(counts.sum().item())
+        self.vocab_of_id = torch.full((n_ids,), -1, dtype=torch.int32, device=dev)
+        self.vocab_of_id[self.order] = torch.arange(V, dtype=torch.int32, device=dev)
+        self.bucket_bits = int(min(20, max(4, int(np.ceil(np.log2(V))) + 2)))
+        self.keep_thr = torch.empty(V, dtype=torch.int32, device=dev)
+        self.cum_table = torch.empty(V, dtype=torch.int32, device=dev)
+        self.bucket_lo = torch.empty((1 << self.bucket_bits) + 1, dtype=torch.int32, device=dev)
+        ws_bytes = int(L.n2v_sgns_prepare_workspace_bytes(C.c_int32(V)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.n2v_sgns_prepare(ptr(self.counts), C.c_int32(V), C.c_double(self.sample), ptr(self.keep_thr),
+                                 ptr(self.cum_table), ptr(self.bucket_lo), C.c_int32(self.bucket_bits),
+                                 ptr(ws), C.c_size_t(ws_bytes), stream()))
+        self.pairs = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.reset_weights()
+
+    def reset_weights(self):
+        dev = self.counts.device
+        self.syn0 = torch.empty((self.V, self.dim), dtype=torch.float32, device=dev)
+        self.syn1neg = torch.empty((self.V, self.dim), dtype=torch.float32, device=dev)
+        check(lib().n2v_sgns_init(ptr(self.syn0), ptr(self.syn1neg), C.c_int32(self.V), C.c_int32(self.dim),
+                                  C.c_uint64(self.seed), stream()))
+
+    def default_hogwild_warps(self) -> int:
+        """Concurrent sentences. gensim runs `workers` (8-12) sentences at a time against the shared
+        tables; the GPU runs thousands. Staleness scales with width/V, so the width is capped at
+        V/4 for small vocabularies (scripts/auc_sweep.py: |dAUC| <= 0.003 up to V/2 with atomic
+        updates) and at the machine width (16 resident warps per SM) otherwise."""
+        sms = int(lib().n2v_sm_count())
+        return int(max(4, min(sms * 16, self.V // 4)))
+
+    def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
+              epoch=0, sent_per_job=125, grid_warps=None, atomic_updates=1, alpha=None, min_alpha=None):
+        """One pass over n_sent sentences (asynchronous on the current stream); self.pairs
+        (device int64) accumulates the (centre, context) pairs trained."""
+        P = SgnsParams()
+        P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
+        P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
+        P.alpha0 = self.alpha if alpha is None else float(alpha)
+        P.min_alpha = self.min_alpha if min_alpha is None else float(min_alpha)
+        P.total_examples, P.example_base = int(total_examples), int(example_base)
+        P.sent_per_job = max(1, int(sent_per_job))
+        P.epoch, P.seed = int(epoch), self.seed
+        P.grid_warps = int(grid_warps or self.default_hogwild_warps())
+        P.atomic_updates = int(atomic_updates)
+        check(lib().n2v_sgns_train(ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride),
+                                   C.c_int64(sent_id_base), ptr(self.vocab_of_id),
+                                   ptr(self.keep_thr if self.sample > 0 else None), ptr(self.cum_table),
+                                   ptr(self.bucket_lo), C.byref(P), ptr(self.syn0), ptr(self.syn1neg),
+                                   ptr(self.pairs), stream()))
+
+
 class Word2Vec:
     """gensim.models.Word2Vec(sg=1, hs=0, negative=k) on the GPU. Signature and defaults are
     gensim 3.2.0's; the reference passes size, window, min_count=0, sg=1, workers, iter."""
@@ -140,7 +214,9 @@ class Word2Vec:
         self.iter, self.batch_words = int(iter), int(batch_words)
         self.sg, self.hs = 1, 0
         self.hogwild_warps = hogwild_warps
-        self.atomic_updates = (int(os.environ.get("N2V_SGNS_ATOMIC", "0")) if atomic_updates is None
+        # row updates: 1 = red.global.add.v4.f32 (no lost updates; measured to keep link-prediction
+        # AUC within 0.003 of the CPU oracle at every Hogwild width), 0 = plain racy stores
+        self.atomic_updates = (int(os.environ.get("N2V_SGNS_ATOMIC", "1")) if atomic_updates is None
                                else int(atomic_updates))
         self.wv = KeyedVectors(self.vector_size)
         self.corpus_count = 0
@@ -191,95 +267,67 @@ class Word2Vec:
 
     def build_vocab(self, sentences, **_):
         """scan_vocab + scale_vocab + finalize_vocab (word2vec.py): count, drop < min_count, sort by
-        count descending (ties: first seen), sub-sampling thresholds, cum_table, reset_weights."""
+        count descending, sub-sampling thresholds, cum_table, reset_weights."""
         dev = require_cuda()
-        L = lib()
         tok, off, stride, n_sent, words = self._ingest(sentences)
         self._corpus = (tok, off, stride, n_sent)
         self.corpus_count = n_sent
         n_ids = len(words)
         counts = torch.zeros(max(n_ids, 1), dtype=torch.int64, device=dev)
-        check(L.n2v_vocab_count(ptr(tok), C.c_int64(tok.numel()), C.c_int32(n_ids), ptr(counts), stream()))
-        counts = counts[:n_ids]
-        keep = counts >= max(self.min_count, 1)
-        # count descending, ties by id: ids are first-seen order for generic corpora and compact node
-        # ids for walk corpora (gensim's tie order is dict order -- unspecified in Python 2)
-        order = torch.sort(torch.where(keep, counts, torch.zeros_like(counts)), descending=True, stable=True).indices
-        V = int(keep.sum().item())
-        if V == 0:
-            raise RuntimeError("you must first build vocabulary before training the model")
-        order = order[:V].contiguous()
-        vcounts = counts[order].contiguous()
-        vocab_of_id = torch.full((n_ids,), -1, dtype=torch.int32, device=dev)
-        vocab_of_id[order] = torch.arange(V, dtype=torch.int32, device=dev)
-        self._vocab_of_id = vocab_of_id
-        self._bucket_bits = int(min(20, max(4, int(np.ceil(np.log2(V))) + 2)))
-        self._keep_thr = torch.empty(V, dtype=torch.int32, device=dev)
-        self._cum_table = torch.empty(V, dtype=torch.int32, device=dev)
-        self._bucket_lo = torch.empty((1 << self._bucket_bits) + 1, dtype=torch.int32, device=dev)
-        ws_bytes = int(L.n2v_sgns_prepare_workspace_bytes(C.c_int32(V)))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(L.n2v_sgns_prepare(ptr(vcounts), C.c_int32(V), C.c_double(self.sample), ptr(self._keep_thr),
-                                 ptr(self._cum_table), ptr(self._bucket_lo), C.c_int32(self._bucket_bits),
-                                 ptr(ws), C.c_size_t(ws_bytes), stream()))
-        self._raw_words = int(counts.sum().item())
+        check(lib().n2v_vocab_count(ptr(tok), C.c_int64(tok.numel()), C.c_int32(n_ids), ptr(counts), stream()))
+        self.trainer = T = SgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
+                                       negative=self.negative, sample=self.sample, seed=self.seed,
+                                       alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
+                                       batch_words=self.batch_words)
         # host-side vocabulary objects (what emb.vocab / index2word expose)
-        order_h, vc_h = order.cpu().numpy(), vcounts.cpu().numpy()
-        kt_h = self._keep_thr.cpu().numpy().view(np.uint32)
+        order_h, vc_h = T.order.cpu().numpy(), T.counts.cpu().numpy()
+        kt_h = T.keep_thr.cpu().numpy().view(np.uint32)
         self.wv.index2word = [words[i] for i in order_h]
         self.wv.vocab = {w: Vocab(i, int(vc_h[i]), int(kt_h[i])) for i, w in enumerate(self.wv.index2word)}
         self.wv.vector_size = self.vector_size
-        self.reset_weights()
+        self.wv._syn0_dev, self.wv._syn0_host = T.syn0, None
+
+    # test/inspection handles
+    @property
+    def _keep_thr(self):
+        return self.trainer.keep_thr
+
+    @property
+    def _cum_table(self):
+        return self.trainer.cum_table
+
+    @property
+    def _bucket_lo(self):
+        return self.trainer.bucket_lo
+
+    @property
+    def _bucket_bits(self):
+        return self.trainer.bucket_bits
+
+    @property
+    def syn1neg_dev(self):
+        return self.trainer.syn1neg
 
     def reset_weights(self):
-        dev = require_cuda()
-        V, d = len(self.wv.index2word), self.vector_size
-        self._syn0 = torch.empty((V, d), dtype=torch.float32, device=dev)
-        self.syn1neg_dev = torch.empty((V, d), dtype=torch.float32, device=dev)
-        check(lib().n2v_sgns_init(ptr(self._syn0), ptr(self.syn1neg_dev), C.c_int32(V), C.c_int32(d),
-                                  C.c_uint64(self.seed), stream()))
-        self.wv._syn0_dev, self.wv._syn0_host = self._syn0, None
+        self.trainer.reset_weights()
+        self.wv._syn0_dev, self.wv._syn0_host = self.trainer.syn0, None
 
     # ---- training ------------------------------------------------------------------------------
-    def default_hogwild_warps(self, V: int) -> int:
-        """Concurrent sentences. gensim runs `workers` (8-12) sentences at a time against the shared
-        tables; the GPU runs thousands. Collisions on the same rows scale with width/V, so the width
-        is capped at V/8 rows-per-warp for small vocabularies and at the machine width otherwise."""
-        sms = int(lib().n2v_sm_count())
-        full = sms * 16
-        return int(max(4, min(full, V // 8)))
-
     def train(self, sentences=None, total_examples=None, total_words=None, epochs=None,
               start_alpha=None, end_alpha=None, **_):
         if sentences is None or isinstance(sentences, tuple):
             tok, off, stride, n_sent = self._corpus if sentences is None else sentences
         else:
             raise NotImplementedError("train() on a new corpus: rebuild the model with that corpus")
+        T = self.trainer
         epochs = self.iter if epochs is None else int(epochs)
-        alpha0 = self.alpha if start_alpha is None else float(start_alpha)
-        min_alpha = self.min_alpha if end_alpha is None else float(end_alpha)
-        V = len(self.wv.index2word)
-        dev = self._syn0.device
-        pairs = torch.zeros(1, dtype=torch.int64, device=dev)
-        mean_len = max(1.0, self._raw_words / max(n_sent, 1))
-        P = SgnsParams()
-        P.V, P.dim, P.window, P.negative = V, self.vector_size, self.window, self.negative
-        P.bucket_bits, P.max_sentence_len = self._bucket_bits, 10000
-        P.alpha0, P.min_alpha = alpha0, min_alpha
-        P.total_examples = int(n_sent) * epochs
-        P.sent_per_job = max(1, int(self.batch_words // mean_len))
-        P.seed = self.seed
-        P.grid_warps = int(self.hogwild_warps or self.default_hogwild_warps(V))
-        P.atomic_updates = int(self.atomic_updates)
+        mean_len = max(1.0, T.raw_words / max(n_sent, 1))
+        before = int(T.pairs.item())
         for ep in range(epochs):
-            P.epoch = ep
-            P.example_base = ep * int(n_sent)
-            check(lib().n2v_sgns_train(ptr(tok), ptr(off), C.c_int64(n_sent), C.c_int32(stride), C.c_int64(0),
-                                       ptr(self._vocab_of_id), ptr(self._keep_thr if self.sample > 0 else None),
-                                       ptr(self._cum_table), ptr(self._bucket_lo), C.byref(P), ptr(self._syn0),
-                                       ptr(self.syn1neg_dev), ptr(pairs), stream()))
-        self.pairs_trained += int(pairs.item())
+            T.train(tok, off, n_sent, stride, total_examples=int(n_sent) * epochs, example_base=ep * int(n_sent),
+                    epoch=ep, sent_per_job=int(self.batch_words // mean_len), grid_warps=self.hogwild_warps,
+                    atomic_updates=self.atomic_updates, alpha=start_alpha, min_alpha=end_alpha)
+        self.pairs_trained += int(T.pairs.item()) - before
         self.train_count += 1
-        self.wv._syn0_dev, self.wv._syn0_host = self._syn0, None
-        self.syn1neg = None
+        self.wv._syn0_dev, self.wv._syn0_host = T.syn0, None
         return self.pairs_trained

@@ -101,9 +101,10 @@ def csr_from_coo(src, dst, w, n_nodes, undirected: bool) -> CSR:
     dst = np.asarray(dst, dtype=np.int64)
     ww = None if w is None else np.asarray(w, dtype=np.float64)
     if undirected:
-        src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
+        # edge i contributes arcs 2i (as given) and 2i+1 (reversed): "last" is by input order
+        src, dst = np.stack([src, dst], 1).ravel(), np.stack([dst, src], 1).ravel()
         if ww is not None:
-            ww = np.concatenate([ww, ww])
+            ww = np.repeat(ww, 2)
     key = src * np.int64(n_nodes) + dst
     order = np.argsort(key, kind="stable")
     key = key[order]

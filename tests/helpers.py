@@ -52,25 +52,38 @@ def chi_square_p(obs, probs):
 
 
 # ---- link-prediction protocol of main_link.main (src/main_link.py:519-565), restated -----------
-def chung_lu_graph(n, m, seed, gamma=0.75, max_deg=None):
+def chung_lu_graph(n, m, seed, gamma=0.75, max_deg=None, communities=1, mu_in=0.8):
     """Heavy-tailed simple undirected graph ("BlogCatalog-shaped"): endpoints
-    drawn with weights ~ (i+10)^-gamma, self-loops/duplicates dropped until m distinct edges."""
+    drawn with weights ~ (i+10)^-gamma (capped so the largest expected degree is ~max_deg),
+    self-loops/duplicates dropped until m distinct edges. communities > 1 plants a partition
+    (node i in community i % communities; an edge stays inside the first endpoint's community
+    with probability mu_in) so that held-out links are predictable from structure -- a pure
+    Chung-Lu graph has none beyond degree, which cosine scores ignore."""
     rng = np.random.RandomState(seed)
     wts = (np.arange(n) + 10.0) ** (-gamma)
     if max_deg:
         wts = np.minimum(wts, wts.sum() * max_deg / (2.0 * m))
     cdf = np.cumsum(wts / wts.sum())
+    comm_nodes = [np.arange(c, n, communities) for c in range(communities)]
+    comm_cdf = [np.cumsum(wts[ix] / wts[ix].sum()) for ix in comm_nodes]
     edges = set()
     while len(edges) < m:
         k = int((m - len(edges)) * 1.3) + 16
-        a = np.searchsorted(cdf, rng.rand(k)); b = np.searchsorted(cdf, rng.rand(k))
+        a = np.searchsorted(cdf, rng.rand(k))
+        b = np.searchsorted(cdf, rng.rand(k))
+        if communities > 1:
+            inside = rng.rand(k) < mu_in
+            u = rng.rand(k)
+            for i in np.nonzero(inside)[0]:
+                c = a[i] % communities
+                b[i] = comm_nodes[c][min(np.searchsorted(comm_cdf[c], u[i]), len(comm_nodes[c]) - 1)]
+        a = np.minimum(a, n - 1); b = np.minimum(b, n - 1)
         for x, y in zip(a.tolist(), b.tolist()):
             if x != y:
                 edges.add((min(x, y), max(x, y)))
                 if len(edges) >= m:
                     break
-    e = np.asarray(sorted(edges), dtype=np.int64)
-    return e
+    return np.asarray(sorted(edges), dtype=np.int64)
 
 
 def split_edges(edges, seed=123, test_ratio=0.5):

@@ -142,11 +142,10 @@ def test_hogwild_auc_matches_oracle():
     """main_link.main protocol (main_link.py:519-565) on a 3k-node heavy-tailed graph: hold out
     50 % of the edges (seed 123), walk the rest (R=5, L=40, p=0.25, q=4), train, score held-out
     edges vs sampled non-edges by cosine, ROC-AUC. Device Hogwild vs the oracle with 8 workers on
-    the SAME corpus, mean of 3 seeds each. Tolerance 0.01 here (small graph, 3 seeds); the
-    north-star +-0.005 / 5 seeds / C2 check is bench_auc.py."""
+    the SAME corpus, mean of 3 seeds each; tolerance = the north-star's +-0.005."""
     from node2vec_by_ecc_b200 import DeviceGraph, WalkCorpus, Word2Vec
     n = 3000
-    edges = chung_lu_graph(n, 60000, seed=42, max_deg=600)
+    edges = chung_lu_graph(n, 60000, seed=42, max_deg=600, communities=20)
     tr, te = split_edges(edges)
     dg = DeviceGraph.from_coo(tr[:, 0], tr[:, 1], None, n, undirected=True)
     t = dg.build_alias_tables(0.25, 4.0)
@@ -167,5 +166,6 @@ def test_hogwild_auc_matches_oracle():
         emb = np.zeros((n, 128), dtype=np.float32)
         emb[voc.index2id] = s0
         auc_ref.append(roc_auc_cosine(emb, te, neg))
-    assert np.mean(auc_ref) > 0.6, auc_ref          # the protocol is learning something
-    assert abs(np.mean(auc_dev) - np.mean(auc_ref)) <= 0.01, (auc_dev, auc_ref)
+    print('AUC device', auc_dev, 'oracle', auc_ref)
+    assert np.mean(auc_ref) > 0.6, (auc_dev, auc_ref)   # the protocol is learning something
+    assert abs(np.mean(auc_dev) - np.mean(auc_ref)) <= 0.005, (auc_dev, auc_ref)

@@ -127,9 +127,11 @@ def test_alias_and_rejection_agree_on_visit_frequencies():
     dg = dev_graph(g, symmetric=True)
     t = dg.build_alias_tables(0.25, 4.0)
     starts = torch.arange(g.n, dtype=torch.int32).repeat(20)
-    wa, _ = dg.walk_alias(t, starts, 40, seed=1)
-    wr, _ = dg.walk_reject(0.25, 4.0, starts, 40, seed=2)
-    fa = np.bincount(wa.cpu().numpy().ravel(), minlength=g.n).astype(np.float64)
-    fr = np.bincount(wr.cpu().numpy().ravel(), minlength=g.n).astype(np.float64)
-    fa, fr = fa / fa.sum(), fr / fr.sum()
-    assert np.abs(fa - fr).sum() < 0.03       # total-variation-ish distance between visit laws
+    def visit_law(walks):
+        f = np.bincount(walks.cpu().numpy().ravel(), minlength=g.n).astype(np.float64)
+        return f / f.sum()
+    fa1 = visit_law(dg.walk_alias(t, starts, 40, seed=1)[0])
+    fa2 = visit_law(dg.walk_alias(t, starts, 40, seed=3)[0])
+    fr = visit_law(dg.walk_reject(0.25, 4.0, starts, 40, seed=2)[0])
+    noise = np.abs(fa1 - fa2).sum()           # sampling noise of the statistic: alias vs alias
+    assert np.abs(fa1 - fr).sum() < 1.5 * noise and np.abs(fa2 - fr).sum() < 1.5 * noise

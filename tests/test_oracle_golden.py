@@ -90,3 +90,20 @@ def test_csr_from_coo_matches_fixture():
     keep = src <= g.col                       # one orientation per undirected edge
     g2 = oracle.csr_from_coo(src[keep], g.col[keep], g.w[keep], g.n, undirected=True)
     assert (g2.row_ptr == g.row_ptr).all() and (g2.col == g.col).all() and (g2.w == g.w).all()
+
+
+def test_csr_from_coo_is_networkx_last_write_wins():
+    import networkx as nx
+    rng = np.random.RandomState(3)
+    n, m = 60, 900
+    a, b, w = rng.randint(0, n, size=m), rng.randint(0, n, size=m), rng.rand(m)
+    for undirected in (True, False):
+        G = nx.Graph() if undirected else nx.DiGraph()
+        G.add_nodes_from(range(n))
+        for x, y, ww in zip(a.tolist(), b.tolist(), w.tolist()):
+            G.add_edge(x, y, weight=ww)
+        g = oracle.csr_from_coo(a, b, w, n, undirected=undirected)
+        for v in range(n):
+            nb = sorted(G.neighbors(v))
+            assert g.col[g.row_ptr[v]:g.row_ptr[v + 1]].tolist() == nb
+            assert g.w[g.row_ptr[v]:g.row_ptr[v + 1]].tolist() == [G[v][x]["weight"] for x in nb]
