@@ -36,24 +36,32 @@ def rmat_edges(scale: int, n_edges: int, seed: int = 1, device="cuda", abcd=(0.5
     """-> (lo int32[M], hi int32[M], n_nodes): M <= n_edges distinct undirected edges lo < hi over
     compacted ids."""
     a, b, c, _ = abcd
-    n_raw = int(n_edges * oversample)
-    keys = []
-    for s in range(0, n_raw, chunk):
-        idx = torch.arange(s, min(s + chunk, n_raw), dtype=torch.int64, device=device)
-        src = torch.zeros_like(idx)
-        dst = torch.zeros_like(idx)
-        for lvl in range(scale):
-            u = hash_uniform(seed, lvl, idx)
-            sb = (u >= a + b).to(torch.int64)                       # quadrants c, d: source bit
-            db = (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)   # quadrants b, d
-            src |= sb << lvl
-            dst |= db << lvl
-        lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
-        keep = lo != hi
-        keys.append((lo[keep] << scale) | hi[keep])
-        del idx, src, dst, lo, hi, keep
-    key = torch.unique(torch.cat(keys))
-    del keys
+    def raw(first, last):
+        out = []
+        for s in range(first, last, chunk):
+            idx = torch.arange(s, min(s + chunk, last), dtype=torch.int64, device=device)
+            src = torch.zeros_like(idx)
+            dst = torch.zeros_like(idx)
+            for lvl in range(scale):
+                u = hash_uniform(seed, lvl, idx)
+                sb = (u >= a + b).to(torch.int64)                       # quadrants c, d: source bit
+                db = (((u >= a) & (u < a + b)) | (u >= a + b + c)).to(torch.int64)   # quadrants b, d
+                src |= sb << lvl
+                dst |= db << lvl
+            lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+            keep = lo != hi
+            out.append((lo[keep] << scale) | hi[keep])
+            del idx, src, dst, lo, hi, keep
+        return out
+
+    done = int(n_edges * oversample)
+    key = torch.unique(torch.cat(raw(0, done)))
+    for _ in range(16):                 # R-MAT repeats edges: top up until n_edges distinct ones
+        if key.numel() >= n_edges:
+            break
+        more = int((n_edges - key.numel()) * 1.5) + 1024
+        key = torch.unique(torch.cat([key] + raw(done, done + more)))
+        done += more
     if key.numel() > n_edges:      # keep a hash-random subset of exactly n_edges
         h = _mix64(key + _wrap(seed * 0x9E3779B97F4A7C15))
         key = key[torch.argsort(h)[:n_edges]]

@@ -270,3 +270,20 @@ def sgns_train(tok_idx, sent_off, vocab: Vocab, dim=128, window=10, negative=5, 
         _p(syn1neg, C.c_float), C.byref(pairs))
     assert rc == 0
     return syn0, syn1neg, int(pairs.value)
+
+
+def vocab_from_counts(counts_by_id, sample: float = 1e-3) -> Vocab:
+    """Vocabulary from given per-id counts (ids with count 0 are absent): count descending,
+    ties by id -- used when the corpus itself is only sampled (bench.py)."""
+    c = np.asarray(counts_by_id, dtype=np.int64)
+    order = np.argsort(-c, kind="stable")
+    V = int((c > 0).sum())
+    order = order[:V].astype(np.int32)
+    counts = np.ascontiguousarray(c[order])
+    id2i = np.full(c.shape[0], -1, dtype=np.int32)
+    id2i[order] = np.arange(V, dtype=np.int32)
+    si = np.zeros(V, dtype=np.uint64)
+    cum = np.zeros(V, dtype=np.uint32)
+    lib().sgns_oracle_prepare(_p(counts, C.c_int64), C.c_int32(V), C.c_double(sample),
+                              _p(si, C.c_uint64), _p(cum, C.c_uint32))
+    return Vocab(counts, order, id2i, si, cum)
