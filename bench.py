@@ -31,6 +31,9 @@ if ROOT not in sys.path:
 
 BYTES_PER_PAIR = 7168        # 2 x 512 B x (1 input + 1 positive + 5 negative rows)
 BYTES_PER_ALIAS_STEP = 40
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the default bench step, from the
+# committed `ncu --set full` captures (profiles/): filled in when a capture exists, else null
+NCU_TRAFFIC = {}
 
 
 def parse():
@@ -52,6 +55,7 @@ def parse():
     ap.add_argument("--walk-mode", default="reject", choices=["reject", "alias"])
     ap.add_argument("--hogwild-warps", type=int, default=0)
     ap.add_argument("--atomic", type=int, default=1)
+    ap.add_argument("--shared-negatives", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -175,13 +179,15 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(counts)
     trainer = SgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
-    grid_warps = a.hogwild_warps or trainer.default_hogwild_warps()
+    grid_warps = a.hogwild_warps or trainer.default_hogwild_warps(bool(a.shared_negatives))
     counters.zero_()
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern = {"walk": [], "sgns": []}
+
+    mode = {"shared": int(a.shared_negatives)}
 
     def step(i, host_io=None, record=False):
         g0 = (i * world + rank) * B                         # global id of this rank's first walk
@@ -198,14 +204,15 @@ def run_ours(a):
             walks.copy_(hw, non_blocking=True)               # takes them back in
         e2.record()
         trainer.train(walks, None, B, L, total_examples=total_walks, example_base=g0 % total_walks,
-                      sent_id_base=g0, sent_per_job=10000 // L, grid_warps=grid_warps,
-                      atomic_updates=a.atomic)
+                      sent_id_base=g0, sent_per_job=10000 // L,
+                      grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
+                      atomic_updates=a.atomic, negative_sharing=mode["shared"])
         e3.record()
         if world > 1:                                        # replicated tables, averaged
             dist.all_reduce(trainer.syn0); dist.all_reduce(trainer.syn1neg)
             trainer.syn0.mul_(1.0 / world); trainer.syn1neg.mul_(1.0 / world)
         if host_io is not None:
-            hp.copy_(trainer.pairs, non_blocking=True)
+            hp.copy_(trainer.pairs[:1], non_blocking=True)
             torch.cuda.current_stream().synchronize()        # the caller reads the result
         if record:
             kern["walk"].append((e0, e1)); kern["sgns"].append((e2, e3))
@@ -217,7 +224,7 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def timed(first_step, host_io=None, record=False):
-        p0 = int(trainer.pairs.item())
+        p0 = trainer.pairs.clone()
         c0 = counters.clone()
         barrier()
         s, e = ev(), ev()
@@ -227,16 +234,16 @@ def run_ours(a):
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
-        pr = torch.tensor([int(trainer.pairs.item()) - p0], dtype=torch.int64, device=dev)
+        pr = trainer.pairs - p0
         cn = counters - c0
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX); dist.all_reduce(pr); dist.all_reduce(cn)
-        return float(ms.item()), int(pr.item()), cn.cpu().numpy()
+        return float(ms.item()), int(pr[0].item()), cn.cpu().numpy(), int(pr[1].item())
 
     for i in range(a.warmup):
         step(i)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, pairs, cn = timed(a.warmup, record=True)
+    ms, pairs, cn, centres = timed(a.warmup, record=True)
     clocks = sampler.stop() if sampler else None
     walk_ms = sum(x.elapsed_time(y) for x, y in kern["walk"])
     sgns_ms = sum(x.elapsed_time(y) for x, y in kern["sgns"])
@@ -252,20 +259,43 @@ def run_ours(a):
         dst = torch.empty(B, dtype=torch.int32, device=dev)
         io = (hs, hw, hl, hp, dst)
         step(a.warmup + a.steps, io)                                        # warm the pinned path
-        ms_e, pairs_e, _ = timed(a.warmup + a.steps + 1, host_io=io)
+        ms_e, pairs_e, _, _ = timed(a.warmup + a.steps + 1, host_io=io)
         e2e = {"value": pairs_e / (ms_e / 1e3), "unit": "pairs/s",
                "h2d_bytes_per_step": (B * 4 + B * L * 4) * world, "d2h_bytes_per_step": (B * L * 4 + B * 4 + 8) * world,
                "ms_per_step": ms_e / a.steps,
                "api": "DeviceGraph.walk_reject -> host -> SgnsTrainer.train (pinned host buffers)"}
 
+    other = None
+    if not a.no_e2e:      # the other negative-sampling mode, same steps, kernel-timed
+        kern_main = kern
+        kern = {"walk": [], "sgns": []}
+        mode["shared"] = 1 - mode["shared"]
+        step(a.warmup + 2 * a.steps + 2)
+        ms_o, pairs_o, _, _ = timed(a.warmup + 2 * a.steps + 3, record=True)
+        sg_o = sum(x.elapsed_time(y) for x, y in kern["sgns"])
+        other = {"shared_negatives": mode["shared"], "value": pairs_o / (ms_o / 1e3), "unit": "pairs/s",
+                 "sgns_pairs_per_s_kernel": pairs_o / (sg_o / 1e3), "ms_per_step": ms_o / a.steps,
+                 "algorithmic_GBps_at_7168B_per_pair": pairs_o / world * BYTES_PER_PAIR / (sg_o / 1e3) / 1e9}
+        mode["shared"] = 1 - mode["shared"]
+        kern = kern_main
+
     out = None
     if rank == 0:
         peak, src = peaks()
-        sg_gbs = my_pairs_rank * BYTES_PER_PAIR / (sgns_ms / 1e3) / 1e9
-        roof = {"kernel": "sgns_train_kernel", "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
-                "frac": sg_gbs / peak, "traffic": None, "peak_source": src,
-                "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "pairs_per_launch": my_pairs_rank / a.steps,
-                "ms_per_launch": sgns_ms / a.steps}
+        if a.shared_negatives:
+            # shared-negative kernel: per pair the input row (read + written, 1,024 B), per centre
+            # the 6 carried output rows (read + written once, 6,144 B)
+            alg_bytes = (my_pairs_rank * 1024.0 + centres / world * 6144.0)
+            kname = "sgns_train_kernel_v3 (shared negatives)"
+        else:
+            alg_bytes = my_pairs_rank * float(BYTES_PER_PAIR)
+            kname = "sgns_train_kernel_v2 (per-pair negatives)"
+        sg_gbs = alg_bytes / (sgns_ms / 1e3) / 1e9
+        roof = {"kernel": kname, "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
+                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]), "peak_source": src,
+                "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / a.steps,
+                "centres_per_launch": centres / world / a.steps, "ms_per_launch": sgns_ms / a.steps,
+                "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (sgns_ms / 1e3) / 1e9}
         if tables is None:
             S, T, P = (float(cn[0]) / world, float(cn[1]) / world, float(cn[3]) / world)
             wbytes = 20 * S + 4 * T + 4 * P
@@ -275,7 +305,7 @@ def run_ours(a):
             wbytes = BYTES_PER_ALIAS_STEP * S
         w_gbs = wbytes / (walk_ms / 1e3) / 1e9
         roof_walk = {"kernel": "walk_%s_kernel" % a.walk_mode, "bound": "hbm", "achieved": w_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": None,
+                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_%s_kernel" % a.walk_mode),
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}
         out = {
@@ -286,8 +316,8 @@ def run_ours(a):
             "config": config_of(a, n, dg.nnz),
             "walk_steps_per_s": (float(cn[0]) if tables is None else S * world) / (walk_ms / 1e3),
             "sgns_pairs_per_s_kernel": pairs / (sgns_ms / 1e3),
-            "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "gpu_launches": 2 * a.steps,
-            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "setup_s": t_setup,
+            "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other, "gpu_launches": 2 * a.steps,
+            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
         }
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a, dg, trainer, walks)
@@ -426,6 +456,10 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
+    # stdout carries exactly one JSON line: anything libraries print (NCCL banners ...) goes to stderr
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -146,13 +146,18 @@ typedef struct {
     uint64_t seed;
     int32_t grid_warps;        /* concurrent warps (Hogwild width); 1 = sequential, deterministic */
     int32_t atomic_updates;    /* 0 = plain stores (gensim's racy Hogwild), 1 = red.global.add */
+    int32_t negative_sharing;  /* 0 = fresh negatives for every (centre, context) pair (gensim);
+                                  1 = one set per centre, shared by its context pairs (dim<=128, k=5) */
+    int32_t tuning;            /* 0 = default. bits 0-1: resident blocks/SM of the d<=128,k=5 kernel
+                                  (1: 4, 2: 8, else 6); bit 3: force the generic kernel */
 } n2v_sgns_params_t;
 
 /* One pass over sentences [0, n_sent): tokens int32 ids (node ids if vocab_of_id != NULL,
  * else vocabulary indices; negative = padding), sentence s = tokens[sent_off[s] ..
  * sent_off[s+1]) or, when sent_off == NULL, the fixed-stride row s of an [n_sent, stride]
  * buffer (a walk buffer). sent_id_base addresses the Philox draws (global sentence id).
- * Updates syn0/syn1neg in place; *pairs_out (device) += (centre, context) pairs trained. */
+ * Updates syn0/syn1neg in place; pairs_out (device uint64[2]): [0] += (centre, context) pairs
+ * trained, [1] += centres whose output rows were carried (negative_sharing mode only). */
 int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
                    int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
                    const uint32_t *keep_thr, const uint32_t *cum_table, const int32_t *bucket_lo,

@@ -265,6 +265,68 @@ struct SgnsArgs {
     float *syn0, *syn1neg; unsigned long long *pairs_out;
 };
 
+struct WarpSentence {       // per-warp staging of the kept tokens of one sentence chunk
+    int32_t *idx; uint16_t *pos; uint8_t *rw;
+};
+
+// job_producer: alpha is fixed per job of whole sentences (word2vec.py train())
+__device__ __forceinline__ float job_alpha(const n2v_sgns_params_t &p, int64_t s)
+{
+    const int64_t ex = p.example_base + s;
+    const int64_t job_first = ex - ex % p.sent_per_job;
+    double prog = (double)job_first / (double)p.total_examples;
+    double al = (double)p.alpha0 - ((double)p.alpha0 - (double)p.min_alpha) * prog;
+    return (float)(al > (double)p.min_alpha ? al : (double)p.min_alpha);
+}
+
+// train_batch_sg prologue: sub-sample + per-position window shrink, compacted in sentence order.
+// Fills the staging arrays from tokens [t_next, tl) until the chunk is full; returns n_kept.
+__device__ __forceinline__ int32_t load_chunk(const SgnsArgs &a, const WarpSentence &ws, int64_t tb, int64_t tl,
+                                              int64_t &t_next, uint64_t gs, uint32_t ep8, uint32_t k0,
+                                              uint32_t k1, int lane)
+{
+    int32_t n_kept = 0;
+    while (t_next < tl && n_kept <= SGNS_SMEM_TOKENS - 32) {
+        const int64_t t = t_next + lane;
+        int32_t wv = -1; uint32_t red = 0;
+        if (t < tl) {
+            int32_t id = a.tokens[tb + t];
+            if (id >= 0) wv = a.vocab_of_id ? __ldg(a.vocab_of_id + id) : id;
+            if (wv >= 0) {
+                const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)t, ep8, k0, k1);
+                if (a.keep_thr && __ldg(a.keep_thr + wv) < r.x) wv = -1;   // sample_int < random_int32
+                red = r.y % (uint32_t)a.p.window;                          // reduced_windows[i]
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, wv >= 0);
+        if (wv >= 0) {
+            const int o = n_kept + __popc(m & ((1u << lane) - 1u));
+            ws.idx[o] = wv; ws.pos[o] = (uint16_t)t; ws.rw[o] = (uint8_t)red;
+        }
+        n_kept += __popc(m);
+        t_next += 32;
+    }
+    __syncwarp();
+    return n_kept;
+}
+
+// lane n (< negative) draws negative n of pair (i, j)
+__device__ __forceinline__ int32_t draw_pair_negatives(const SgnsArgs &a, const WarpSentence &ws, int32_t i,
+                                                       int32_t j, uint64_t gs, uint32_t ep8, uint32_t k0,
+                                                       uint32_t k1, int lane)
+{
+    int32_t my_t = -1;
+    if (lane < a.p.negative) {
+        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32),
+                                        ((uint32_t)ws.pos[i] << 16) | (uint32_t)ws.pos[j],
+                                        ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
+        const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+        my_t = draw_negative(rr, a.cum_table, a.bucket_lo, a.p.V, a.p.bucket_bits);
+    }
+    return my_t;
+}
+
+// ---- v1: generic kernel (any dim <= 1024, any negative <= 16), one pair at a time ------------------
 // NV = float4 chunks per lane (dim <= 128*NV). ATOMIC selects red.global.add.v4.f32 updates.
 template <int NV, bool ATOMIC>
 __global__ void __launch_bounds__(SGNS_BLOCK)
@@ -278,13 +340,11 @@ sgns_train_kernel(SgnsArgs a)
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int32_t *idx = s_idx[wib];
-    uint16_t *pos = s_pos[wib];
-    uint8_t *rw = s_rw[wib];
+    const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = a.p.grid_warps;
     if (warp >= n_warps) return;
-    const int32_t dim = a.p.dim, window = a.p.window, negative = a.p.negative, V = a.p.V;
+    const int32_t dim = a.p.dim, window = a.p.window, negative = a.p.negative;
     const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
     const uint32_t ep8 = a.p.epoch << 8;
     bool act[NV];
@@ -297,59 +357,19 @@ sgns_train_kernel(SgnsArgs a)
         int64_t tl = a.sent_off ? a.sent_off[s + 1] - tb : (int64_t)a.stride;
         if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
-        // job_producer: alpha fixed per job of whole sentences (word2vec.py train())
-        const int64_t ex = a.p.example_base + s;
-        const int64_t job_first = ex - ex % a.p.sent_per_job;
-        float alpha;
-        {
-            double prog = (double)job_first / (double)a.p.total_examples;
-            double al = (double)a.p.alpha0 - ((double)a.p.alpha0 - (double)a.p.min_alpha) * prog;
-            alpha = (float)(al > (double)a.p.min_alpha ? al : (double)a.p.min_alpha);
-        }
-        // --- sub-sample + window shrink, compacted in sentence order (train_batch_sg prologue).
+        const float alpha = job_alpha(a.p, s);
         // Sentences longer than the staging buffer are processed in chunks of kept tokens.
         int64_t t_next = 0;
         while (t_next < tl) {
-            int32_t n_kept = 0;
-            while (t_next < tl && n_kept <= SGNS_SMEM_TOKENS - 32) {
-                const int64_t t = t_next + lane;
-                int32_t wv = -1; uint32_t red = 0;
-                if (t < tl) {
-                    int32_t id = a.tokens[tb + t];
-                    if (id >= 0) wv = a.vocab_of_id ? __ldg(a.vocab_of_id + id) : id;
-                    if (wv >= 0) {
-                        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (uint32_t)t, ep8, k0, k1);
-                        if (a.keep_thr && __ldg(a.keep_thr + wv) < r.x) wv = -1;   // sample_int < random_int32
-                        red = r.y % (uint32_t)window;                              // reduced_windows[i]
-                    }
-                }
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, wv >= 0);
-                if (wv >= 0) {
-                    const int o = n_kept + __popc(m & ((1u << lane) - 1u));
-                    idx[o] = wv; pos[o] = (uint16_t)t; rw[o] = (uint8_t)red;
-                }
-                n_kept += __popc(m);
-                t_next += 32;
-            }
-            __syncwarp();
-            // --- pairs
+            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
             for (int32_t i = 0; i < n_kept; ++i) {
-                const int32_t centre = idx[i];
-                int32_t j = i - window + rw[i]; if (j < 0) j = 0;
-                int32_t kend = i + window + 1 - rw[i]; if (kend > n_kept) kend = n_kept;
+                const int32_t centre = ws.idx[i];
+                int32_t j = i - window + ws.rw[i]; if (j < 0) j = 0;
+                int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 for (; j < kend; ++j) {
                     if (j == i) continue;
-                    const int32_t ctx = idx[j];
-                    // negatives: lane n draws negative n
-                    int32_t my_t = -1;
-                    if (lane < negative) {
-                        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32),
-                                                        ((uint32_t)pos[i] << 16) | (uint32_t)pos[j],
-                                                        ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
-                        const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
-                        my_t = draw_negative(rr, a.cum_table, a.bucket_lo, V, a.p.bucket_bits);
-                    }
-                    train_pair<NV, ATOMIC>(a.syn0, a.syn1neg, dim, centre, ctx, my_t, negative, alpha, act, s_exp, lane);
+                    const int32_t my_t = draw_pair_negatives(a, ws, i, j, gs, ep8, k0, k1, lane);
+                    train_pair<NV, ATOMIC>(a.syn0, a.syn1neg, dim, centre, ws.idx[j], my_t, negative, alpha, act, s_exp, lane);
                     ++pairs;
                 }
             }
@@ -359,6 +379,312 @@ sgns_train_kernel(SgnsArgs a)
     if (lane == 0 && a.pairs_out && pairs) atomicAdd(a.pairs_out, pairs);
 }
 
+// ---- v2: the reference configuration (dim <= 128, negative == 5) --------------------------------
+// Same arithmetic in the same order as v1 / fast_sentence_sg_neg, restructured for latency:
+//  * centre-major: syn1neg[centre] (the positive target of every pair of a centre) is read once,
+//    carried in registers across the ~10 context pairs and written back as ONE reduction -- no other
+//    pair of this warp can touch that row meanwhile (negatives equal to the centre are skipped);
+//  * the negative draws of pair k+1 (Philox -> bucket index -> bisect, 3-4 dependent L2 reads) are
+//    issued between the row loads of pair k and their first use, off the critical path;
+//  * rows are loaded with ld.global.cg (no reuse inside an SM; RED updates happen at L2).
+__device__ __forceinline__ float4 ldcg4(const float *row, int lane)
+{
+    return __ldcg(reinterpret_cast<const float4 *>(row) + lane);
+}
+__device__ __forceinline__ float dot4(const float4 &x, const float4 &y)
+{
+    return x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+}
+__device__ __forceinline__ void axpy4(float4 &acc, float g, const float4 &x)
+{
+    acc.x += g * x.x; acc.y += g * x.y; acc.z += g * x.z; acc.w += g * x.w;
+}
+template <bool ATOMIC>
+__device__ __forceinline__ void add_row(float *row, int lane, const float4 &delta, const float4 &updated, bool on)
+{
+    if (!on) return;
+    float4 *p = reinterpret_cast<float4 *>(row) + lane;
+    if (ATOMIC) atomicAdd(p, delta); else *p = updated;
+}
+
+template <bool ATOMIC, int MINB>
+__global__ void __launch_bounds__(SGNS_BLOCK, MINB)
+sgns_train_kernel_v2(SgnsArgs a)
+{
+    constexpr int FN = 5;
+    __shared__ int32_t s_idx[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ float s_exp[EXP_TABLE_SIZE];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = a.p.grid_warps;
+    if (warp >= n_warps) return;
+    const int32_t dim = a.p.dim, window = a.p.window;
+    const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
+    const uint32_t ep8 = a.p.epoch << 8;
+    const bool on = lane * 4 < dim;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *const syn0 = a.syn0, *const syn1neg = a.syn1neg;
+    unsigned long long pairs = 0;
+
+    for (int64_t s = warp; s < a.n_sent; s += n_warps) {
+        const int64_t tb = a.sent_off ? a.sent_off[s] : s * (int64_t)a.stride;
+        int64_t tl = a.sent_off ? a.sent_off[s + 1] - tb : (int64_t)a.stride;
+        if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
+        const uint64_t gs = (uint64_t)(a.sent_id_base + s);
+        const float alpha = job_alpha(a.p, s);
+        int64_t t_next = 0;
+        while (t_next < tl) {
+            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
+            // pair cursor (i, j) in gensim's order: centres ascending, contexts ascending, j != i
+            int32_t i = -1, j = 0, kend = 0;
+            auto seek = [&]() -> bool {
+                for (;;) {
+                    if (i >= n_kept) return false;
+                    if (j < kend) { if (j != i) return true; ++j; continue; }
+                    if (++i >= n_kept) return false;
+                    j = i - window + ws.rw[i]; if (j < 0) j = 0;
+                    kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
+                }
+            };
+            bool more = seek();
+            int32_t t_cur = more ? draw_pair_negatives(a, ws, i, j, gs, ep8, k0, k1, lane) : -1;
+            int32_t carried = -1;                        // vocabulary index of the carried centre row
+            int32_t carried_i = -1;
+            float4 pos_row = zero4, pos_delta = zero4;
+            while (more) {
+                const int32_t centre = ws.idx[i], ctx = ws.idx[j];
+                if (i != carried_i) {                    // new centre: write the old row back, fetch the new one
+                    if (carried >= 0) add_row<ATOMIC>(syn1neg + (int64_t)carried * dim, lane, pos_delta, pos_row, on);
+                    carried = centre; carried_i = i;
+                    pos_row = on ? ldcg4(syn1neg + (int64_t)centre * dim, lane) : zero4;
+                    pos_delta = zero4;
+                }
+                // B: all rows of this pair in flight
+                float *const row1p = syn0 + (int64_t)ctx * dim;
+                const float4 row1 = on ? ldcg4(row1p, lane) : zero4;
+                int32_t tg[FN];
+                float4 r2[FN];
+                bool dup = false;
+#pragma unroll
+                for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_cur, d);
+#pragma unroll
+                for (int d1 = 0; d1 < FN; ++d1)
+#pragma unroll
+                    for (int d2 = d1 + 1; d2 < FN; ++d2) dup |= (tg[d1] == tg[d2]);
+#pragma unroll
+                for (int d = 0; d < FN; ++d)
+                    r2[d] = (on && tg[d] != centre) ? ldcg4(syn1neg + (int64_t)tg[d] * dim, lane) : zero4;
+                // A (next pair): advance the cursor, draw its negatives while the rows arrive
+                ++j;
+                more = seek();
+                const int32_t t_nxt = more ? draw_pair_negatives(a, ws, i, j, gs, ep8, k0, k1, lane) : -1;
+                // C: fast_sentence_sg_neg, targets in order: centre (label 1), then the negatives
+                float4 work = zero4;
+                float f[FN + 1];
+                f[0] = dot4(row1, pos_row);
+#pragma unroll
+                for (int d = 0; d < FN; ++d) f[d + 1] = dot4(row1, r2[d]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int d = 0; d <= FN; ++d) f[d] += __shfl_xor_sync(0xFFFFFFFFu, f[d], o);
+                if (f[0] > -(float)MAX_EXP && f[0] < (float)MAX_EXP) {
+                    const float g = (1.0f - s_exp[(int)((f[0] + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
+                    axpy4(work, g, pos_row);                                  // work += g * syn1neg[centre]
+                    axpy4(pos_row, g, row1); axpy4(pos_delta, g, row1);       // syn1neg[centre] += g * row1
+                }
+                if (!dup) {
+#pragma unroll
+                    for (int d = 0; d < FN; ++d) {
+                        if (tg[d] == centre) continue;                        // skipped, not redrawn
+                        if (f[d + 1] <= -(float)MAX_EXP || f[d + 1] >= (float)MAX_EXP) continue;
+                        const float g = (0.0f - s_exp[(int)((f[d + 1] + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
+                        axpy4(work, g, r2[d]);
+                        float4 upd = r2[d];
+                        axpy4(upd, g, row1);
+                        add_row<ATOMIC>(syn1neg + (int64_t)tg[d] * dim, lane,
+                                        make_float4(g * row1.x, g * row1.y, g * row1.z, g * row1.w), upd, on);
+                    }
+                } else {
+                    // a repeated negative must see the row as updated by its first occurrence
+                    for (int d = 0; d < FN; ++d) {
+                        const int32_t t = __shfl_sync(0xFFFFFFFFu, t_cur, d);
+                        if (t == centre) continue;
+                        float *const rp = syn1neg + (int64_t)t * dim;
+                        const float4 row2 = on ? ldcg4(rp, lane) : zero4;
+                        const float ff = warp_sum(dot4(row1, row2));
+                        if (ff <= -(float)MAX_EXP || ff >= (float)MAX_EXP) continue;
+                        const float g = (0.0f - s_exp[(int)((ff + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
+                        axpy4(work, g, row2);
+                        float4 upd = row2;
+                        axpy4(upd, g, row1);
+                        add_row<ATOMIC>(rp, lane, make_float4(g * row1.x, g * row1.y, g * row1.z, g * row1.w), upd, on);
+                    }
+                }
+                float4 upd1 = row1;
+                upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
+                add_row<ATOMIC>(row1p, lane, work, upd1, on);                  // syn0[ctx] += work
+                ++pairs;
+                t_cur = t_nxt;
+            }
+            if (carried >= 0) add_row<ATOMIC>(syn1neg + (int64_t)carried * dim, lane, pos_delta, pos_row, on);
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && a.pairs_out && pairs) atomicAdd(a.pairs_out, pairs);
+}
+
+// ---- v3: one negative set per centre, shared by its context pairs ------------------------------
+// (north-star subsystem 4: "staging of the shared negative set"; pWord2Vec-style sharing).
+// The (1 positive + 5 negative) output rows of a centre are read ONCE, carried in registers across
+// the centre's ~10 context pairs -- each pair runs fast_sentence_sg_neg's arithmetic in order
+// against the carried rows -- and written back as one reduction per row. Per pair only the input
+// row syn0[context] moves: 1,024 B + 6,144 B / pairs-per-centre instead of 7,168 B. Distribution
+// of negatives per pair is unchanged (count^0.75); only their independence across one window is
+// given up. Negative sets with a repeated row fall back to the uncarried sequential form.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(SGNS_BLOCK, 4)
+sgns_train_kernel_v3(SgnsArgs a)
+{
+    constexpr int FN = 5;
+    __shared__ int32_t s_idx[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
+    __shared__ float s_exp[EXP_TABLE_SIZE];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = a.p.grid_warps;
+    if (warp >= n_warps) return;
+    const int32_t dim = a.p.dim, window = a.p.window;
+    const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
+    const uint32_t ep8 = a.p.epoch << 8;
+    const bool on = lane * 4 < dim;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *const syn0 = a.syn0, *const syn1neg = a.syn1neg;
+    unsigned long long pairs = 0, centres = 0;
+
+    // lane n draws shared negative n of centre position i: Philox ctr (pos_i << 16 | 0xFFFF)
+    auto draw_centre = [&](int32_t i, uint64_t gs) -> int32_t {
+        int32_t t = -1;
+        if (lane < FN) {
+            const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), ((uint32_t)ws.pos[i] << 16) | 0xFFFFu,
+                                            ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
+            const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+            t = draw_negative(rr, a.cum_table, a.bucket_lo, a.p.V, a.p.bucket_bits);
+        }
+        return t;
+    };
+    auto sigmoid_g = [&](float f, float label, float alpha) -> float {
+        return (label - s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
+    };
+
+    for (int64_t s = warp; s < a.n_sent; s += n_warps) {
+        const int64_t tb = a.sent_off ? a.sent_off[s] : s * (int64_t)a.stride;
+        int64_t tl = a.sent_off ? a.sent_off[s + 1] - tb : (int64_t)a.stride;
+        if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
+        const uint64_t gs = (uint64_t)(a.sent_id_base + s);
+        const float alpha = job_alpha(a.p, s);
+        int64_t t_next = 0;
+        while (t_next < tl) {
+            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
+            // centres that have at least one context pair, in order; negatives drawn one centre ahead
+            auto bounds = [&](int32_t i, int32_t &j0, int32_t &kend) -> bool {
+                j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
+                kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
+                return (kend - j0) > ((i >= j0 && i < kend) ? 1 : 0);
+            };
+            int32_t i = 0, j0 = 0, kend = 0;
+            while (i < n_kept && !bounds(i, j0, kend)) ++i;
+            int32_t t_cur = i < n_kept ? draw_centre(i, gs) : -1;
+            while (i < n_kept) {
+                const int32_t centre = ws.idx[i];
+                ++centres;
+                int32_t tg[FN];
+                bool dup = false;
+#pragma unroll
+                for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_cur, d);
+#pragma unroll
+                for (int d1 = 0; d1 < FN; ++d1)
+#pragma unroll
+                    for (int d2 = d1 + 1; d2 < FN; ++d2) dup |= (tg[d1] == tg[d2]) && (tg[d1] != centre);
+                // next centre with pairs + its negatives (off the critical path)
+                int32_t ni = i + 1, nj0 = 0, nkend = 0;
+                while (ni < n_kept && !bounds(ni, nj0, nkend)) ++ni;
+                if (!dup) {
+                    float4 out[FN + 1], delta[FN + 1];
+                    out[0] = on ? ldcg4(syn1neg + (int64_t)centre * dim, lane) : zero4;
+#pragma unroll
+                    for (int d = 0; d < FN; ++d)
+                        out[d + 1] = (on && tg[d] != centre) ? ldcg4(syn1neg + (int64_t)tg[d] * dim, lane) : zero4;
+#pragma unroll
+                    for (int d = 0; d <= FN; ++d) delta[d] = zero4;
+                    int32_t j = (j0 == i) ? j0 + 1 : j0;
+                    float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
+                    const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
+                    while (j < kend) {
+                        const int32_t ctx = ws.idx[j];
+                        int32_t jn = j + 1; if (jn == i) ++jn;
+                        // next input row in flight unless it is the row this pair is about to update
+                        const bool pre = jn < kend && ws.idx[jn] != ctx;
+                        float4 row1n = zero4;
+                        if (pre && on) row1n = ldcg4(syn0 + (int64_t)ws.idx[jn] * dim, lane);
+                        float f[FN + 1];
+#pragma unroll
+                        for (int d = 0; d <= FN; ++d) f[d] = dot4(row1, out[d]);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                            for (int d = 0; d <= FN; ++d) f[d] += __shfl_xor_sync(0xFFFFFFFFu, f[d], o);
+                        float4 work = zero4;
+#pragma unroll
+                        for (int d = 0; d <= FN; ++d) {
+                            if (d > 0 && tg[d - 1] == centre) continue;               // skipped, not redrawn
+                            if (f[d] <= -(float)MAX_EXP || f[d] >= (float)MAX_EXP) continue;
+                            const float g = sigmoid_g(f[d], d == 0 ? 1.0f : 0.0f, alpha);
+                            axpy4(work, g, out[d]);
+                            axpy4(out[d], g, row1); axpy4(delta[d], g, row1);
+                        }
+                        float4 upd1 = row1;
+                        upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
+                        add_row<ATOMIC>(syn0 + (int64_t)ctx * dim, lane, work, upd1, on);
+                        ++pairs;
+                        j = jn;
+                        if (j < kend) row1 = pre ? row1n : (on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4);
+                    }
+                    add_row<ATOMIC>(syn1neg + (int64_t)centre * dim, lane, delta[0], out[0], on);
+#pragma unroll
+                    for (int d = 0; d < FN; ++d)
+                        if (tg[d] != centre) add_row<ATOMIC>(syn1neg + (int64_t)tg[d] * dim, lane, delta[d + 1], out[d + 1], on);
+                    t_cur = t_nxt;
+                } else {
+                    // repeated row in the set: uncarried sequential form (every target re-read per pair)
+                    const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
+                    const bool act1[1] = {on};
+                    for (int32_t j = j0; j < kend; ++j) {
+                        if (j == i) continue;
+                        train_pair<1, ATOMIC>(syn0, syn1neg, dim, centre, ws.idx[j], t_cur, FN, alpha, act1, s_exp, lane);
+                        ++pairs;
+                    }
+                    t_cur = t_nxt;
+                }
+                i = ni; j0 = nj0; kend = nkend;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, centres); }
+}
+
 template <int NV>
 static int launch_train(const SgnsArgs &a, cudaStream_t stream)
 {
@@ -366,6 +692,17 @@ static int launch_train(const SgnsArgs &a, cudaStream_t stream)
     const int blocks = (a.p.grid_warps + warps_per_block - 1) / warps_per_block;
     if (a.p.atomic_updates) sgns_train_kernel<NV, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
     else sgns_train_kernel<NV, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+template <int MINB>
+static int launch_train_v2(const SgnsArgs &a, cudaStream_t stream)
+{
+    const int warps_per_block = SGNS_BLOCK / 32;
+    const int blocks = (a.p.grid_warps + warps_per_block - 1) / warps_per_block;
+    if (a.p.atomic_updates) sgns_train_kernel_v2<true, MINB><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+    else sgns_train_kernel_v2<false, MINB><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
     N2V_LAUNCH_CHECK();
     return N2V_OK;
 }
@@ -472,6 +809,21 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
     SgnsArgs a{tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table,
                bucket_lo, p, syn0, syn1neg, pairs_out};
     const int nv = (p.dim + 127) / 128;
+    if (p.negative_sharing) {
+        N2V_REQUIRE(nv == 1 && p.negative == 5, "negative_sharing needs dim <= 128 and negative == 5");
+        const int blocks = (p.grid_warps + SGNS_BLOCK / 32 - 1) / (SGNS_BLOCK / 32);
+        if (p.atomic_updates) sgns_train_kernel_v3<true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        else sgns_train_kernel_v3<false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        N2V_LAUNCH_CHECK();
+        return N2V_OK;
+    }
+    if (nv == 1 && p.negative == 5 && !(p.tuning & 8)) {      // reference configuration: v2
+        switch (p.tuning & 3) {
+            case 1: return launch_train_v2<4>(a, stream);
+            case 2: return launch_train_v2<8>(a, stream);
+            default: return launch_train_v2<6>(a, stream);
+        }
+    }
     switch (nv) {
         case 1: return launch_train<1>(a, stream);
         case 2: return launch_train<2>(a, stream);

@@ -214,7 +214,7 @@ static int64_t run_job(train_ctx_t *c, int64_t job, int32_t *indexes, int32_t *o
     const float alpha = c->job_alpha[job];
     const int64_t n_sent = c->n_sent;
     uint64_t next_random = 0, sm = c->seed * 0x9E3779B97F4A7C15ull + (uint64_t)job;
-    if (c->rng_mode == 0) next_random = splitmix64(&sm) & 281474976710655ull;   /* 2^24*r1+r2 */
+    if ((c->rng_mode & 1) == 0) next_random = splitmix64(&sm) & 281474976710655ull;   /* 2^24*r1+r2 */
 
     int64_t eff_words = 0, eff_sent = 0;
     sidx[0] = 0;
@@ -227,7 +227,7 @@ static int64_t run_job(train_ctx_t *c, int64_t job, int32_t *indexes, int32_t *o
             if (w < 0) continue;                                  /* not in vocab / padding */
             if (c->sample_int) {
                 uint64_t r32;
-                if (c->rng_mode == 0) {
+                if ((c->rng_mode & 1) == 0) {
                     next_random = (next_random * 25214903917ull + 11ull) & 281474976710655ull;
                     r32 = next_random >> 16;
                 } else {
@@ -238,7 +238,7 @@ static int64_t run_job(train_ctx_t *c, int64_t job, int32_t *indexes, int32_t *o
             }
             indexes[eff_words] = w;
             origpos[eff_words] = (int32_t)(t - b);
-            if (c->rng_mode == 0) redwin[eff_words] = (int32_t)(splitmix64(&sm) % (uint64_t)c->window);
+            if ((c->rng_mode & 1) == 0) redwin[eff_words] = (int32_t)(splitmix64(&sm) % (uint64_t)c->window);
             else {
                 uint32_t r[4]; philox_words(c->seed, (uint64_t)gs, (uint32_t)(t - b), epoch << 8, r);
                 redwin[eff_words] = (int32_t)(r[1] % (uint32_t)c->window);
@@ -264,23 +264,28 @@ static int64_t run_job(train_ctx_t *c, int64_t job, int32_t *indexes, int32_t *o
             if (j < is) j = is;
             int64_t k = i + c->window + 1 - redwin[i];
             if (k > ie) k = ie;
+            int fresh = 1;
             for (; j < k; ++j) {
                 if (j == i) continue;
                 uint32_t rr[4] = {0, 0, 0, 0};
-                for (int32_t n = 0; n < c->negative; ++n) {
+                /* rng_mode bit 1: ONE negative set per centre position, shared by all its context
+                 * pairs (the device's shared-negative mode; not gensim's behaviour) */
+                const int share = (c->rng_mode & 2) != 0;
+                for (int32_t n = 0; n < c->negative && !(share && !fresh); ++n) {
                     uint32_t r32;
-                    if (c->rng_mode == 0) {
+                    if ((c->rng_mode & 1) == 0) {
                         r32 = (uint32_t)(next_random >> 16);
                         next_random = (next_random * 25214903917ull + 11ull) & 281474976710655ull;
                     } else {
                         if ((n & 3) == 0)
                             philox_words(c->seed, (uint64_t)gs,
-                                         ((uint32_t)origpos[i] << 16) | (uint32_t)origpos[j],
+                                         ((uint32_t)origpos[i] << 16) | (share ? 0xFFFFu : (uint32_t)origpos[j]),
                                          (epoch << 8) | (uint32_t)(1 + (n >> 2)), rr);
                         r32 = rr[n & 3];
                     }
                     neg[n] = bisect_left_u32(c->cum_table, c->V, r32 % cum_last);
                 }
+                fresh = 0;
                 sg_neg_pair(c, indexes[i], indexes[j], neg, alpha, work);
                 ++pairs;
             }

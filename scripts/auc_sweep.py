@@ -25,16 +25,17 @@ def auc_of(m_):
     emb[np.asarray([int(w) for w in m_.wv.index2word])] = m_.wv.syn0
     return roc_auc_cosine(emb, te, neg)
 
+shared = int(os.environ.get("SWEEP_SHARED", "0"))
 for atomic in (0, 1):
     for wdt in widths:
         aucs = []
         for seed in (1, 2, 3):
             torch.cuda.synchronize(); t0 = time.time()
             mm = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, seed=seed,
-                          hogwild_warps=wdt, atomic_updates=atomic)
+                          hogwild_warps=wdt, atomic_updates=atomic, shared_negatives=shared)
             torch.cuda.synchronize(); dt = time.time() - t0
             aucs.append(auc_of(mm))
-        print(f"atomic={atomic} width={wdt} auc={np.round(aucs, 4)} mean={np.mean(aucs):.4f} pairs={mm.pairs_trained} t={dt:.2f}s", flush=True)
+        print(f"shared={shared} atomic={atomic} width={wdt} auc={np.round(aucs, 4)} mean={np.mean(aucs):.4f} pairs={mm.pairs_trained} t={dt:.2f}s", flush=True)
 
 voc = oracle.sgns_vocab(walks_np, n)
 tok = voc.id2index[np.maximum(walks_np, 0)].astype(np.int32); tok[walks_np < 0] = -1

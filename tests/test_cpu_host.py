@@ -1,0 +1,141 @@
+"""CPU: the C-ABI library loads and exports every symbol include/n2v_b200.h declares (no compute
+without a GPU: compute calls must fail loudly), host-side logic, and the N>1 sharding/averaging
+logic under gloo with world_size 2."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from node2vec_by_ecc_b200 import SO_PATH, lib
+    from node2vec_by_ecc_b200._lib import EXPORTS
+    hdr = open(os.path.join(ROOT, "include", "n2v_b200.h")).read()
+    declared = set(re.findall(r"\b(n2v_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    L = lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.n2v_version() >= 100
+    assert os.path.dirname(SO_PATH).endswith("node2vec_by_ecc_b200")      # built in-tree
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from node2vec_by_ecc_b200 import DeviceGraph, Graph, N2VError, Word2Vec, lib
+    import networkx as nx
+    with pytest.raises(N2VError):
+        DeviceGraph.from_coo([0], [1], None, 2, undirected=True)
+    G = Graph(nx.path_graph(4), False, 1, 1)
+    with pytest.raises(N2VError):
+        G.preprocess_transition_probs()
+    with pytest.raises(N2VError):
+        Word2Vec([["a", "b"]], sg=1, min_count=0)
+    # the C entry points themselves refuse without a device
+    assert lib().n2v_sm_count() < 0
+    rc = lib().n2v_walk_alias(*([ctypes.c_void_p(8)] * 6), ctypes.c_int64(1), ctypes.c_int32(4),
+                              ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_void_p(8), ctypes.c_void_p(8),
+                              ctypes.c_void_p(0))
+    assert rc < 0 and b"CUDA" in lib().n2v_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "node2vec_by_ecc_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+                assert "libn2v_oracle" not in src, f
+
+
+def test_line_sentence_and_keyedvectors_host_logic(tmp_path):
+    from node2vec_by_ecc_b200 import KeyedVectors, LineSentence, Vocab
+    p = tmp_path / "w.txt"
+    p.write_text("1 2 3\n\n4 5\n" + " ".join(str(i) for i in range(25)) + "\n")
+    s = list(LineSentence(str(p), max_sentence_length=10))
+    assert s[0] == ["1", "2", "3"] and s[1] == ["4", "5"]      # empty lines yield nothing (gensim)
+    assert [len(x) for x in s[2:]] == [10, 10, 5]
+    assert list(LineSentence(str(p), limit=1)) == [["1", "2", "3"]]
+    kv = KeyedVectors(4)
+    kv.index2word = ["a", "b"]
+    kv.vocab = {"a": Vocab(0, 5), "b": Vocab(1, 3)}
+    kv.syn0 = np.asarray([[1, 0, 0, 0], [1, 1, 0, 0]], dtype=np.float32)
+    assert abs(kv.similarity("a", "b") - 2 ** -0.5) < 1e-6 and kv["b"].tolist() == [1, 1, 0, 0]
+    assert kv[["a", "b"]].shape == (2, 4) and "a" in kv and "z" not in kv
+    with pytest.raises(KeyError):
+        kv["z"]
+    out = tmp_path / "e.txt"
+    kv.save_word2vec_format(str(out))
+    assert out.read_text().splitlines()[0] == "2 4"
+
+
+def test_walk_corpus_sequence_view():
+    from node2vec_by_ecc_b200 import WalkCorpus
+    labels = np.asarray([10, 20, 30, 40])
+    w = torch.tensor([[0, 1, 2], [3, -1, -1]], dtype=torch.int32)
+    c = WalkCorpus(w, torch.tensor([3, 1], dtype=torch.int32), labels)
+    assert len(c) == 2 and c[0] == [10, 20, 30] and c[1] == [40] and c[-1] == [40]
+    assert [list(map(str, x)) for x in c] == [["10", "20", "30"], ["40"]]
+    c.extend(WalkCorpus(w[:1], torch.tensor([2], dtype=torch.int32), labels))
+    assert len(c) == 3 and c[2] == [10, 20] and c.num_steps() == 3
+
+
+def test_shard_range_matches_main_link_partition():
+    from node2vec_by_ecc_b200.dist import shard_range, step_walk_ids
+    import math
+    for total in (0, 1, 7, 34, 100, 101):
+        for world in (1, 2, 3, 6, 8):
+            parts = [shard_range(total, r, world) for r in range(world)]
+            # main_link.py:263-264: split_point = range(0, len, ceil(len/num_pool)) + [len]
+            covered = [i for a, b in parts for i in range(a, b)]
+            assert covered == list(range(total))
+            if total:
+                per = int(math.ceil(float(total) / world))
+                assert all(b - a == per for a, b in parts if b < total)
+    ids = sorted(step_walk_ids(s, r, 4, 8) for s in range(3) for r in range(4))
+    assert ids == list(range(0, 96, 8))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from node2vec_by_ecc_b200.dist import average_tables, shard_range, sum_counts
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    a, b = shard_range(10, rank, world)
+    counts = torch.zeros(10, dtype=torch.int64)
+    counts[a:b] = torch.arange(a, b) + 1
+    sum_counts(counts)
+    t0 = torch.full((4, 8), float(rank + 1))
+    t1 = torch.full((4, 8), float(10 * (rank + 1)))
+    average_tables(t0, t1)
+    q.put((rank, counts.tolist(), float(t0[0, 0]), float(t1[0, 0])))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_counts_and_table_averaging():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, counts, a0, a1 in res:
+        assert counts == list(range(1, 11))          # disjoint shards summed
+        assert a0 == 1.5 and a1 == 15.0              # (1+2)/2, (10+20)/2

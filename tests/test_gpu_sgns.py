@@ -84,7 +84,7 @@ def test_sequential_device_run_equals_oracle(size, negative, iters, sample):
     from node2vec_by_ecc_b200 import Word2Vec
     z, g, corpus = corpus_from_golden("karate_p025_q4")
     m = Word2Vec(corpus, size=size, window=10, min_count=0, sg=1, iter=iters, negative=negative,
-                 sample=sample, seed=1, hogwild_warps=1)
+                 sample=sample, seed=1, hogwild_warps=1, shared_negatives=0)
     tok, off, voc = oracle_inputs(m, z["walks"])
     s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=size, window=10, negative=negative, iters=iters,
                                       workers=1, rng_mode=1, seed=1, subsample=sample > 0)
@@ -95,11 +95,38 @@ def test_sequential_device_run_equals_oracle(size, negative, iters, sample):
     assert np.abs(s0).max() > 0.05            # training moved the rows well away from init
 
 
+@pytest.mark.parametrize("size,iters,sample,case", [(128, 1, 1e-3, "rndw_p05_q2"), (64, 2, 0.0, "karate_p4_q025"),
+                                                   (100, 1, 1e-2, "karate_p1_q1")])
+def test_shared_negative_mode_sequential_equals_oracle(size, iters, sample, case):
+    """shared_negatives=1 (one negative set per centre, output rows carried in registers across its
+    context pairs) == the oracle's shared mode (rng_mode 3 = Philox | shared) run by one worker."""
+    from node2vec_by_ecc_b200 import Word2Vec
+    z, g, corpus = corpus_from_golden(case)
+    m = Word2Vec(corpus, size=size, window=10, min_count=0, sg=1, iter=iters, negative=5, sample=sample,
+                 seed=3, hogwild_warps=1, shared_negatives=1)
+    tok, off, voc = oracle_inputs(m, z["walks"])
+    s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=size, window=10, negative=5, iters=iters,
+                                      workers=1, rng_mode=3, seed=3, subsample=sample > 0)
+    assert m.pairs_trained == pairs and pairs > 1000
+    d0 = np.abs(m.wv.syn0 - s0).max()
+    d1 = np.abs(m.syn1neg_dev.cpu().numpy() - s1).max()
+    assert d0 < 2e-4 and d1 < 2e-4, (d0, d1)
+    # and it is a different stream of negatives than the per-pair mode
+    s0p, _, _ = oracle.sgns_train(tok, off, voc, dim=size, window=10, negative=5, iters=iters,
+                                  workers=1, rng_mode=1, seed=3, subsample=sample > 0)
+    assert np.abs(s0p - s0).max() > 1e-3
+
+
 def test_atomic_update_mode_sequential_equals_plain():
     from node2vec_by_ecc_b200 import Word2Vec
     _, _, corpus = corpus_from_golden()
     a = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1, atomic_updates=0)
     b = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1, atomic_updates=1)
+    c = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1, atomic_updates=0,
+                 shared_negatives=0)
+    d = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1, atomic_updates=1,
+                 shared_negatives=0)
+    assert np.abs(c.wv.syn0 - d.wv.syn0).max() < 2e-4
     assert np.abs(a.wv.syn0 - b.wv.syn0).max() < 2e-4
 
 
@@ -138,7 +165,8 @@ def test_unsupported_modes_raise():
         Word2Vec([["a", "b"]], sg=1, hs=1, negative=0)
 
 
-def test_hogwild_auc_matches_oracle():
+@pytest.mark.parametrize("shared", [0, 1])
+def test_hogwild_auc_matches_oracle(shared):
     """main_link.main protocol (main_link.py:519-565) on a 3k-node heavy-tailed graph: hold out
     50 % of the edges (seed 123), walk the rest (R=5, L=40, p=0.25, q=4), train, score held-out
     edges vs sampled non-edges by cosine, ROC-AUC. Device Hogwild vs the oracle with 8 workers on
@@ -156,7 +184,8 @@ def test_hogwild_auc_matches_oracle():
     walks_np = walks.cpu().numpy()
     auc_dev, auc_ref = [], []
     for seed in (1, 2, 3):
-        m = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, workers=8, iter=1, seed=seed)
+        m = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, workers=8, iter=1, seed=seed,
+                     shared_negatives=shared)
         emb = np.zeros((n, 128), dtype=np.float32)
         emb[np.asarray([int(w) for w in m.wv.index2word])] = m.wv.syn0
         auc_dev.append(roc_auc_cosine(emb, te, neg))
