@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--window", type=int, default=10)
     ap.add_argument("--negative", type=int, default=5)
     ap.add_argument("--walk-mode", default="reject", choices=["reject", "alias"])
+    ap.add_argument("--walk-indexed", type=int, default=1, help="1 = hashed distance-1 test + state machine")
     ap.add_argument("--hogwild-warps", type=int, default=0)
     ap.add_argument("--atomic", type=int, default=1)
     ap.add_argument("--shared-negatives", type=int, default=1)
@@ -164,7 +165,8 @@ def run_ours(a):
         if tables is not None:
             dg.walk_alias(tables, starts, L, 1, base, out=(walks, lens))
         else:
-            dg.walk_reject(a.p, a.q, starts, L, 1, base, counters=counters, out=(walks, lens))
+            dg.walk_reject(a.p, a.q, starts, L, 1, base, counters=counters, out=(walks, lens),
+                           indexed=bool(a.walk_indexed))
 
     # vocabulary (scan_vocab): one walk per node, this rank's contiguous shard, counts summed
     counts = torch.zeros(n, dtype=torch.int64, device=dev)
@@ -304,7 +306,7 @@ def run_ours(a):
             T = P = 0.0
             wbytes = BYTES_PER_ALIAS_STEP * S
         w_gbs = wbytes / (walk_ms / 1e3) / 1e9
-        roof_walk = {"kernel": "walk_%s_kernel" % a.walk_mode, "bound": "hbm", "achieved": w_gbs, "peak": peak,
+        roof_walk = {"kernel": ("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode), "bound": "hbm", "achieved": w_gbs, "peak": peak,
                      "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_%s_kernel" % a.walk_mode),
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}

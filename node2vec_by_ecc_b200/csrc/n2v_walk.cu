@@ -14,6 +14,7 @@
 //                 :142-150) with pre-accept / pre-reject bounds and the return edge folded out as
 //                 an outlier; needs no edge tables (graphs whose Sigma deg^2 does not fit).
 #include "n2v_common.cuh"
+#include "n2v_reject.cuh"
 
 namespace n2v {
 
@@ -83,18 +84,6 @@ walk_alias_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict
 }
 
 // ---- rejection mode ----------------------------------------------------------------------------
-struct RejectParams {
-    uint32_t t_ret, t_in, t_out;   // accept iff r < t_x ; thresholds = alpha_x / B * 2^32 (saturated)
-    uint32_t t_lo, t_hi;           // pre-accept below t_lo; (x != prev) pre-reject at/above t_hi
-    int fold;                      // return edge folded out as an outlier (unweighted, symmetric)
-    double fold_mass, bound;       // (1/p - B') and B' = max(1, 1/q)
-};
-
-__device__ __forceinline__ uint32_t ceil_log2_p1(int64_t deg)   // ceil(log2(deg+1))
-{
-    return deg <= 0 ? 0u : (uint32_t)(64 - __clzll((unsigned long long)deg));
-}
-
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(WALK_BLOCK)
 walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
@@ -186,14 +175,6 @@ walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
     }
 }
 
-static uint32_t to_thr(double x)   // x in [0,1] -> ceil(x * 2^32) saturated
-{
-    double t = ceil(x * 4294967296.0);
-    if (t >= 4294967296.0) return 0xFFFFFFFFu;
-    if (t <= 0.0) return 0u;
-    return (uint32_t)t;
-}
-
 }  // namespace n2v
 
 using namespace n2v;
@@ -231,19 +212,7 @@ extern "C" int n2v_walk_reject(const int64_t *row_ptr, const int32_t *col, const
     N2V_REQUIRE(row_ptr && col && starts && walks && lens, "NULL buffer");
     N2V_REQUIRE(!w || node_slots, "weighted graph needs node_slots");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    const double a_ret = 1.0 / p, a_in = 1.0, a_out = 1.0 / q;
-    RejectParams rp;
-    const double b_rest = a_in > a_out ? a_in : a_out;
-    rp.fold = (!w && symmetric && a_ret > b_rest) ? 1 : 0;
-    rp.bound = rp.fold ? b_rest : (a_ret > b_rest ? a_ret : b_rest);
-    rp.fold_mass = rp.fold ? a_ret - b_rest : 0.0;
-    const double r_ret = (rp.fold ? b_rest : a_ret) / rp.bound;
-    rp.t_ret = to_thr(r_ret);
-    rp.t_in = to_thr(a_in / rp.bound);
-    rp.t_out = to_thr(a_out / rp.bound);
-    uint32_t lo = rp.t_ret < rp.t_in ? rp.t_ret : rp.t_in;
-    rp.t_lo = lo < rp.t_out ? lo : rp.t_out;
-    rp.t_hi = rp.t_in > rp.t_out ? rp.t_in : rp.t_out;
+    const RejectParams rp = make_reject_params(p, q, w != nullptr, symmetric);
     const int64_t blocks = (n_walks + WALK_BLOCK - 1) / WALK_BLOCK;
     N2V_REQUIRE(blocks < 2147483647ll, "too many walks for one launch");
     if (w)

@@ -215,10 +215,31 @@ class DeviceGraph:
                                    ptr(lens), stream()))
         return walks, lens
 
+    def reject_index(self):
+        """(packed_rows uint64[N], edge_hash uint64[cap], cap) for n2v_walk_reject_indexed, built
+        once per graph; None when a degree / offset does not fit the packed row word."""
+        if "rix" not in self._cache:
+            L = lib()
+            dev = self.device
+            packed = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            check(L.n2v_pack_rows(ptr(self.row_ptr), C.c_int32(self.n), ptr(packed), ptr(flag), stream()))
+            if int(flag.item()):
+                self._cache["rix"] = None
+            else:
+                cap = int(L.n2v_edge_hash_capacity(C.c_int64(self.nnz)))
+                table = torch.empty(cap, dtype=torch.int64, device=dev)
+                check(L.n2v_edge_hash_build(ptr(self.row_ptr), ptr(self.col), C.c_int32(self.n), C.c_int64(self.nnz),
+                                            ptr(table), C.c_uint64(cap), stream()))
+                self._cache["rix"] = (packed, table, cap)
+        return self._cache["rix"]
+
     def walk_reject(self, p: float, q: float, starts: torch.Tensor, L_: int, seed: int,
                     walk_id_base: int = 0, node_tables: AliasTables | None = None, counters=None,
-                    out=None):
-        """Same law as get_alias_edge (node2vec.py:142-150) by rejection sampling; no edge tables."""
+                    out=None, indexed: bool = True):
+        """Same law as get_alias_edge (node2vec.py:142-150) by rejection sampling; no edge tables.
+        indexed=True uses the hashed distance-1 test + per-lane state machine (n2v_walk_reject_indexed,
+        16 bytes per arc of index), False the binary-search form (n2v_walk_reject, no extra memory)."""
         starts = torch.as_tensor(starts, dtype=torch.int32).to(self.device).contiguous()
         n = int(starts.shape[0])
         if self.w is not None and node_tables is None:
@@ -226,6 +247,16 @@ class DeviceGraph:
         walks, lens = out if out is not None else (
             torch.empty((n, L_), dtype=torch.int32, device=self.device),
             torch.empty(n, dtype=torch.int32, device=self.device))
+        rix = self.reject_index() if indexed else None
+        if rix is not None:
+            packed, table, cap = rix
+            check(lib().n2v_walk_reject_indexed(
+                ptr(packed), ptr(self.col), C.c_int64(self.nnz), ptr(self.w),
+                ptr(node_tables.node_slots if node_tables is not None else None), ptr(table), C.c_uint64(cap),
+                C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts), C.c_int64(n),
+                C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base), ptr(walks), ptr(lens), ptr(counters),
+                stream()))
+            return walks, lens
         check(lib().n2v_walk_reject(ptr(self.row_ptr), ptr(self.col), ptr(self.w),
                                     ptr(node_tables.node_slots if node_tables is not None else None),
                                     C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts),

@@ -72,7 +72,8 @@ def transition_counts(walks, lens, n):
 @pytest.mark.parametrize("weighted,directed,p,q", [(False, False, 0.25, 4.0), (False, False, 4.0, 0.25),
                                                     (False, False, 1.0, 1.0), (True, False, 0.25, 4.0),
                                                     (True, True, 0.5, 2.0), (False, True, 4.0, 0.5)])
-def test_rejection_walker_chi_square(weighted, directed, p, q):
+@pytest.mark.parametrize("indexed", [True, False])
+def test_rejection_walker_chi_square(weighted, directed, p, q, indexed):
     n = 300
     _, g = random_graph(n, 3000, seed=31, weighted=weighted, directed=directed, skew=1.0)
     dg = dev_graph(g, symmetric=not directed)
@@ -82,7 +83,7 @@ def test_rejection_walker_chi_square(weighted, directed, p, q):
     starts_np = np.concatenate([np.full(400000, hub, dtype=np.int32),
                                 np.repeat(np.arange(n, dtype=np.int32), 2000)])
     counters = torch.zeros(4, dtype=torch.int64, device="cuda")
-    walks, lens = dg.walk_reject(p, q, torch.as_tensor(starts_np), 3, seed=99, counters=counters)
+    walks, lens = dg.walk_reject(p, q, torch.as_tensor(starts_np), 3, seed=99, counters=counters, indexed=indexed)
     cnt = counters.cpu().numpy()
     assert cnt[0] == int((lens.cpu().numpy() - 1).sum()) and cnt[1] >= cnt[0]
     keys, c = transition_counts(walks, lens, n)
@@ -109,6 +110,52 @@ def test_rejection_walker_chi_square(weighted, directed, p, q):
     # 60 independent tests: no catastrophic cell, and the p-values are not piled up near 0
     assert pvals.min() > 1e-5, pvals.min()
     assert (pvals < 0.01).sum() <= 4, np.sort(pvals)[:6]
+
+
+def test_edge_hash_holds_exactly_the_arcs():
+    _, g = random_graph(500, 6000, seed=17, directed=True, skew=0.8)
+    dg = dev_graph(g, symmetric=False)
+    packed, table, cap = dg.reject_index()
+    assert cap >= 2 * g.nnz and cap & (cap - 1) == 0
+    t = table.cpu().numpy().view(np.uint64)
+    keys = np.sort(t[t != np.uint64(0xFFFFFFFFFFFFFFFF)])
+    src = np.repeat(np.arange(g.n, dtype=np.uint64), np.diff(g.row_ptr))
+    want = np.sort((src << np.uint64(32)) | g.col.astype(np.uint64))
+    assert np.array_equal(keys, want)
+    pk = packed.cpu().numpy().view(np.uint64)
+    assert np.array_equal(pk >> np.uint64(24), g.row_ptr[:-1].astype(np.uint64))
+    assert np.array_equal(pk & np.uint64((1 << 24) - 1), np.diff(g.row_ptr).astype(np.uint64))
+
+
+@pytest.mark.parametrize("L", [1, 2, 7, 8, 9, 33, 80])
+def test_indexed_rejection_walk_shapes_and_dead_ends(L):
+    """ragged lengths, -1 padding, every consecutive pair is an arc -- both rejection forms"""
+    _, g = random_graph(400, 1500, seed=23, directed=True, skew=0.5)     # sparse: plenty of sinks
+    dg = dev_graph(g, symmetric=False)
+    starts = torch.arange(g.n, dtype=torch.int32).repeat(3)
+    arcs = set(zip(np.repeat(np.arange(g.n), np.diff(g.row_ptr)).tolist(), g.col.tolist()))
+    deg = np.diff(g.row_ptr)
+    for indexed in (True, False):
+        walks, lens = dg.walk_reject(0.5, 2.0, starts, L, seed=4, indexed=indexed)
+        w, l = walks.cpu().numpy(), lens.cpu().numpy()
+        assert w.shape == (starts.shape[0], L) and (w[:, 0] == starts.numpy()).all()
+        for row, ln in zip(w[:200], l[:200]):
+            assert 1 <= ln <= L and (row[ln:] == -1).all() and (row[:ln] >= 0).all()
+            assert all((int(a), int(b)) in arcs for a, b in zip(row[:ln - 1], row[1:ln]))
+            assert ln == L or deg[row[ln - 1]] == 0          # stops early only at a dead end
+
+
+@pytest.mark.parametrize("weighted,directed", [(False, False), (True, False), (True, True)])
+def test_both_rejection_forms_make_identical_walks(weighted, directed):
+    """same Philox words, same decisions: the hashed/state-machine form reproduces the
+    binary-search form token by token"""
+    _, g = random_graph(2000, 30000, seed=41, weighted=weighted, directed=directed, skew=1.0)
+    dg = dev_graph(g, symmetric=not directed)
+    starts = torch.arange(g.n, dtype=torch.int32).repeat(2)
+    c1 = torch.zeros(4, dtype=torch.int64, device="cuda"); c2 = torch.zeros_like(c1)
+    a, la = dg.walk_reject(0.25, 4.0, starts, 40, seed=6, walk_id_base=77, counters=c1, indexed=False)
+    b, lb = dg.walk_reject(0.25, 4.0, starts, 40, seed=6, walk_id_base=77, counters=c2, indexed=True)
+    assert torch.equal(a, b) and torch.equal(la, lb) and torch.equal(c1, c2)
 
 
 def test_rejection_first_step_follows_node_table():
