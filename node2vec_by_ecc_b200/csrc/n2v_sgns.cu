@@ -621,13 +621,16 @@ sgns_train_kernel_v3(SgnsArgs a)
                 int32_t ni = i + 1, nj0 = 0, nkend = 0;
                 while (ni < n_kept && !bounds(ni, nj0, nkend)) ++ni;
                 if (!dup) {
-                    float4 out[FN + 1], delta[FN + 1];
+                    float4 out[FN + 1], orig[FN + 1];
+                    uint32_t skipmask = 0xC0u;                 // padding targets 6, 7
                     out[0] = on ? ldcg4(syn1neg + (int64_t)centre * dim, lane) : zero4;
 #pragma unroll
                     for (int d = 0; d < FN; ++d)
                         out[d + 1] = (on && tg[d] != centre) ? ldcg4(syn1neg + (int64_t)tg[d] * dim, lane) : zero4;
 #pragma unroll
-                    for (int d = 0; d <= FN; ++d) delta[d] = zero4;
+                    for (int d = 0; d < FN; ++d) if (tg[d] == centre) skipmask |= 2u << d;   // skipped, not redrawn
+#pragma unroll
+                    for (int d = 0; d <= FN; ++d) orig[d] = out[d];
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
                     float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
                     const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
@@ -638,21 +641,39 @@ sgns_train_kernel_v3(SgnsArgs a)
                         const bool pre = jn < kend && ws.idx[jn] != ctx;
                         float4 row1n = zero4;
                         if (pre && on) row1n = ldcg4(syn0 + (int64_t)ws.idx[jn] * dim, lane);
-                        float f[FN + 1];
-#pragma unroll
-                        for (int d = 0; d <= FN; ++d) f[d] = dot4(row1, out[d]);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                            for (int d = 0; d <= FN; ++d) f[d] += __shfl_xor_sync(0xFFFFFFFFu, f[d], o);
+                        // 6 dot products, reduced by a transposing butterfly: after the rounds on lane
+                        // bits 4,3,2 each lane holds ONE of the (padded) 8 sums, bits 1,0 finish it:
+                        // 9 shuffles instead of 30, and the sigmoid is evaluated once per target
+                        // (in the 4 lanes that own it) instead of 6 times per lane.
+                        float a0, a1, a2, a3;
+                        {
+                            const float p0 = dot4(row1, out[0]), p1 = dot4(row1, out[1]), p2 = dot4(row1, out[2]),
+                                        p3 = dot4(row1, out[3]), p4 = dot4(row1, out[4]), p5 = dot4(row1, out[5]);
+                            const bool h = lane & 16;
+                            a0 = (h ? p4 : p0) + __shfl_xor_sync(0xFFFFFFFFu, h ? p0 : p4, 16);
+                            a1 = (h ? p5 : p1) + __shfl_xor_sync(0xFFFFFFFFu, h ? p1 : p5, 16);
+                            a2 = (h ? 0.f : p2) + __shfl_xor_sync(0xFFFFFFFFu, h ? p2 : 0.f, 16);
+                            a3 = (h ? 0.f : p3) + __shfl_xor_sync(0xFFFFFFFFu, h ? p3 : 0.f, 16);
+                        }
+                        float fv;
+                        {
+                            const bool h8 = lane & 8, h4 = lane & 4;
+                            const float b0 = (h8 ? a2 : a0) + __shfl_xor_sync(0xFFFFFFFFu, h8 ? a0 : a2, 8);
+                            const float b1 = (h8 ? a3 : a1) + __shfl_xor_sync(0xFFFFFFFFu, h8 ? a1 : a3, 8);
+                            fv = (h4 ? b1 : b0) + __shfl_xor_sync(0xFFFFFFFFu, h4 ? b0 : b1, 4);
+                            fv += __shfl_xor_sync(0xFFFFFFFFu, fv, 2);
+                            fv += __shfl_xor_sync(0xFFFFFFFFu, fv, 1);
+                        }
+                        // lane owns target v = lane >> 2 (0 = centre, 1..5 = negatives, 6,7 = padding)
+                        float gv = 0.0f;
+                        if (!((skipmask >> (lane >> 2)) & 1u) && fv > -(float)MAX_EXP && fv < (float)MAX_EXP)
+                            gv = sigmoid_g(fv, lane < 4 ? 1.0f : 0.0f, alpha);
                         float4 work = zero4;
 #pragma unroll
-                        for (int d = 0; d <= FN; ++d) {
-                            if (d > 0 && tg[d - 1] == centre) continue;               // skipped, not redrawn
-                            if (f[d] <= -(float)MAX_EXP || f[d] >= (float)MAX_EXP) continue;
-                            const float g = sigmoid_g(f[d], d == 0 ? 1.0f : 0.0f, alpha);
-                            axpy4(work, g, out[d]);
-                            axpy4(out[d], g, row1); axpy4(delta[d], g, row1);
+                        for (int d = 0; d <= FN; ++d) {       // g == 0: target skipped or |f| >= 6 (no-op)
+                            const float g = __shfl_sync(0xFFFFFFFFu, gv, d * 4);
+                            axpy4(work, g, out[d]);           // work += g * syn1neg[t]
+                            axpy4(out[d], g, row1);           // syn1neg[t] += g * row1 (carried)
                         }
                         float4 upd1 = row1;
                         upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
@@ -661,10 +682,14 @@ sgns_train_kernel_v3(SgnsArgs a)
                         j = jn;
                         if (j < kend) row1 = pre ? row1n : (on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4);
                     }
-                    add_row<ATOMIC>(syn1neg + (int64_t)centre * dim, lane, delta[0], out[0], on);
+                    // one reduction per carried row: what this centre's pairs added to it
 #pragma unroll
-                    for (int d = 0; d < FN; ++d)
-                        if (tg[d] != centre) add_row<ATOMIC>(syn1neg + (int64_t)tg[d] * dim, lane, delta[d + 1], out[d + 1], on);
+                    for (int d = 0; d <= FN; ++d) {
+                        if ((skipmask >> d) & 1u) continue;
+                        const float4 dl = make_float4(out[d].x - orig[d].x, out[d].y - orig[d].y,
+                                                      out[d].z - orig[d].z, out[d].w - orig[d].w);
+                        add_row<ATOMIC>(syn1neg + (int64_t)(d == 0 ? centre : tg[d - 1]) * dim, lane, dl, out[d], on);
+                    }
                     t_cur = t_nxt;
                 } else {
                     // repeated row in the set: uncarried sequential form (every target re-read per pair)
