@@ -82,9 +82,10 @@ int n2v_alias_build_nodes(const int64_t *row_ptr, const int32_t *col, const doub
  * preprocess_transition_probs (:194-199). Builds the tables of arcs [arc_begin, arc_end) into
  * slots[etab_ptr[e] ...]; work_J/work_q hold etab_ptr[arc_end]-etab_ptr[arc_begin] entries
  * (pass full-size arrays and keep them to read the reference's raw (J, q) back).
- * symmetric != 0 promises an undirected (symmetric) CSR. */
+ * symmetric != 0 promises an undirected (symmetric) CSR. popwalk != 0 builds get_alias_edge_pop
+ * instead (node2vec.py:154-174: weight / len(G[nbr]), return edge additionally / p, no q). */
 int n2v_alias_build_edges(const int64_t *row_ptr, const int32_t *col, const double *w,
-                          int32_t n_nodes, double p, double q, int symmetric,
+                          int32_t n_nodes, double p, double q, int symmetric, int popwalk,
                           const int64_t *etab_ptr, int64_t arc_begin, int64_t arc_end,
                           n2v_slot_t *slots, int32_t *work_J, double *work_q, void *stream);
 
@@ -182,6 +183,13 @@ int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sen
                    const uint32_t *keep_thr, const uint32_t *cum_table, const int32_t *bucket_lo,
                    const n2v_sgns_params_t *params, float *syn0, float *syn1neg,
                    unsigned long long *pairs_out, void *stream);
+
+/* ---- link scoring ---------------------------------------------------------------------------
+ * replaces: link_score(emb, a, b) with link_method "cos" (src/main_link.py:43-49) over a batch of
+ * pairs, as looped by get_roc_score (:173-189). a/b: row indices (-1 = word not in vocabulary ->
+ * score 0, the reference's except branch). emb float32[V, dim], dim % 4 == 0. */
+int n2v_cosine_pairs(const float *emb, int32_t dim, const int32_t *a, const int32_t *b,
+                     int64_t n_pairs, float *out, void *stream);
 
 /* ---- measurement helpers -------------------------------------------------------------------
  * Random-access HBM roofline denominators: mode 0 = one random 32-byte sector

@@ -115,7 +115,7 @@ alias_nodes_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
 __global__ void __launch_bounds__(256)
 alias_edges_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                    const double *__restrict__ w, int32_t n_nodes, double p, double q, int symmetric,
-                   const int64_t *__restrict__ etab_ptr, int64_t arc_begin, int64_t arc_end,
+                   int popwalk, const int64_t *__restrict__ etab_ptr, int64_t arc_begin, int64_t arc_end,
                    n2v_slot_t *__restrict__ slots, int32_t *__restrict__ work_J,
                    double *__restrict__ work_q)
 {
@@ -136,7 +136,12 @@ alias_edges_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
             const int32_t nbr = col[b + k];
             const double wt = w ? w[b + k] : 1.0;
             double u;
-            if (nbr == src) u = __ddiv_rn(wt, p);                                  // :142-143
+            if (popwalk) {
+                // get_alias_edge_pop (:154-174): pop = len(G[dst_nbr]); w/(p*pop) for the return
+                // edge, w/pop otherwise (both other branches, q does not appear)
+                const double pop = (double)(row_ptr[nbr + 1] - row_ptr[nbr]);
+                u = (nbr == src) ? __ddiv_rn(wt, __dmul_rn(p, pop)) : __ddiv_rn(wt, pop);
+            } else if (nbr == src) u = __ddiv_rn(wt, p);                           // :142-143
             else {
                 // G.has_edge(dst_nbr, src) (:144): arc nbr->src. On a symmetric CSR that is
                 // nbr in adj(src): one row for the whole table, cache friendly.
@@ -216,7 +221,7 @@ extern "C" int n2v_alias_build_nodes(const int64_t *row_ptr, const int32_t *col,
 }
 
 extern "C" int n2v_alias_build_edges(const int64_t *row_ptr, const int32_t *col, const double *w,
-                                     int32_t n_nodes, double p, double q, int symmetric,
+                                     int32_t n_nodes, double p, double q, int symmetric, int popwalk,
                                      const int64_t *etab_ptr, int64_t arc_begin, int64_t arc_end,
                                      n2v_slot_t *slots, int32_t *work_J, double *work_q,
                                      void *stream_)
@@ -228,7 +233,7 @@ extern "C" int n2v_alias_build_edges(const int64_t *row_ptr, const int32_t *col,
     N2V_REQUIRE(row_ptr && col && etab_ptr && slots && work_J && work_q, "NULL buffer");
     int grid = table_grid(arc_end - arc_begin);
     if (grid < 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    alias_edges_kernel<<<grid, 256, 0, stream>>>(row_ptr, col, w, n_nodes, p, q, symmetric, etab_ptr,
+    alias_edges_kernel<<<grid, 256, 0, stream>>>(row_ptr, col, w, n_nodes, p, q, symmetric, popwalk, etab_ptr,
                                                  arc_begin, arc_end, slots, work_J, work_q);
     N2V_LAUNCH_CHECK();
     return N2V_OK;

@@ -165,8 +165,9 @@ class DeviceGraph:
         return t
 
     def build_alias_tables(self, p: float, q: float, popwalk=False, keep_raw=False,
-                           chunk_entries: int = 1 << 27) -> AliasTables:
-        """preprocess_transition_probs (node2vec.py:176-204) on the device."""
+                           chunk_entries: int = 1 << 27, pop_edges=False) -> AliasTables:
+        """preprocess_transition_probs (node2vec.py:176-204) on the device. popwalk: popularity node
+        tables (:213-218); pop_edges: get_alias_edge_pop edge tables (:154-174, the on-the-fly law)."""
         L = lib()
         dev = self.device
         t = self.build_node_tables(popwalk=popwalk, keep_raw=keep_raw)
@@ -193,7 +194,7 @@ class DeviceGraph:
                 wJ = torch.empty(max(ne, 1), dtype=torch.int32, device=dev)
                 wq = torch.empty(max(ne, 1), dtype=torch.float64, device=dev)
             check(L.n2v_alias_build_edges(ptr(self.row_ptr), ptr(self.col), ptr(self.w), C.c_int32(self.n),
-                                          C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)),
+                                          C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), C.c_int(int(pop_edges)),
                                           ptr(etab), C.c_int64(a), C.c_int64(b), ptr(t.edge_slots),
                                           ptr(wJ), ptr(wq), stream()))
         if keep_raw:

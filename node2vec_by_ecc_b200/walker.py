@@ -56,6 +56,20 @@ class WalkCorpus(Sequence):
         out.extend(other)
         return out
 
+    def save_walks(self, path, mode="w"):
+        """The walk file of main_link.py:237-239,544-546: one walk per line, tokens (original
+        labels) joined by single spaces -- what LineSentence / `-walk-path` read back."""
+        w, l = self._h()
+        lab = self.labels
+        with open(path, mode) as f:
+            full = l == w.shape[1]
+            if lab is not None and lab.dtype != object and np.issubdtype(lab.dtype, np.integer) and full.all():
+                np.savetxt(f, lab[w], fmt="%d", delimiter=" ")
+            else:
+                for i in range(w.shape[0]):
+                    row = w[i, :l[i]]
+                    f.write(" ".join(map(str, row.tolist() if lab is None else lab[row].tolist())) + "\n")
+
     # -- list-of-lists view
     def _h(self):
         if self._host is None:
@@ -205,6 +219,7 @@ class Graph:
     def preprocess_transition_probs(self):
         """node2vec.py:176-204. Node tables always; edge tables when they fit (else the walks use
         the rejection sampler, which needs none)."""
+        self._otf_key = None
         self._tables = self._build(False, edges=self._use_alias())
         self._tables_raw = None
         self.alias_nodes = _TableView(self, edges=False)
@@ -213,6 +228,7 @@ class Graph:
 
     def preprocess_transition_probs_popularity(self):
         """node2vec.py:206-237: popularity-normalised node tables, plain edge tables (:228-232)."""
+        self._otf_key = None
         self._tables = self._build(True, edges=self._use_alias())
         self._tables_raw = None
         self.alias_nodes = _TableView(self, edges=False)
@@ -254,12 +270,18 @@ class Graph:
     def simulate_walks_on_the_fly(self, num_walks, walk_length, nodes=None, verbose=False):
         """node2vec.py:97-111: same walks without a prior preprocess call. popwalk "pop" follows
         get_alias_nodes_cur / get_alias_edge_pop (:13-32,:154-174), whose edge law ignores q."""
-        if self.popwalk == "pop":
-            raise NotImplementedError("popwalk='pop' on-the-fly walks (get_alias_edge_pop) are not built yet")
-        key = ("otf", float(self.p), float(self.q))
-        if self._tables is None or getattr(self, "_otf_key", None) != key or self._tables.popwalk:
-            self._dg
-            self._tables = self._build(False, edges=self._use_alias())
+        pop = self.popwalk == "pop"
+        key = ("otf", float(self.p), float(self.q), pop)
+        if self._tables is None or getattr(self, "_otf_key", None) != key:
+            dg = self._dg
+            if pop:
+                # popularity law: tables only (its rejection form is not built); they must fit
+                if dg.edge_table_bytes() * 2.5 > self._table_budget() and self.mode != "alias":
+                    raise NotImplementedError("popwalk='pop' needs edge alias tables and they do not fit "
+                                              "N2V_TABLE_BUDGET_GB on this graph")
+                self._tables = dg.build_alias_tables(float(self.p), float(self.q), popwalk=True, pop_edges=True)
+            else:
+                self._tables = self._build(False, edges=self._use_alias())
             self._tables_raw = None
             self._otf_key = key
         return self._simulate(num_walks, walk_length, nodes, self._tables, verbose)

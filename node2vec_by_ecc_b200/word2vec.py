@@ -99,6 +99,23 @@ class KeyedVectors:
         a, b = self.word_vec(w1), self.word_vec(w2)
         return float(np.dot(a / np.linalg.norm(a), b / np.linalg.norm(b)))
 
+    def similarity_pairs(self, pairs):
+        """Batched link_score 'cos' (main_link.py:43-49) for an iterable of (a, b) words on the
+        device (n2v_cosine_pairs): float32[n]; a pair with a word missing from the vocabulary
+        scores 0, like the reference's except branch. What get_roc_score (:173-189) loops over."""
+        dev = require_cuda()
+        pairs = list(pairs)
+        v = self.vocab
+        ia = np.fromiter((v[a].index if a in v else -1 for a, _ in pairs), dtype=np.int32, count=len(pairs))
+        ib = np.fromiter((v[b].index if b in v else -1 for _, b in pairs), dtype=np.int32, count=len(pairs))
+        emb = self._syn0_dev if self._syn0_dev is not None else torch.as_tensor(self._syn0_host).to(dev)
+        emb = emb.contiguous()
+        da, db = torch.as_tensor(ia).to(dev), torch.as_tensor(ib).to(dev)
+        out = torch.empty(len(pairs), dtype=torch.float32, device=dev)
+        check(lib().n2v_cosine_pairs(ptr(emb), C.c_int32(emb.shape[1]), ptr(da), ptr(db), C.c_int64(len(pairs)),
+                                     ptr(out), stream()))
+        return out.cpu().numpy()
+
     def most_similar(self, positive, topn=10):
         if isinstance(positive, (str, bytes)):
             positive = [positive]

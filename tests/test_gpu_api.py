@@ -79,3 +79,73 @@ def test_graph_survives_pickle():
     G.preprocess_transition_probs()
     G2 = pickle.loads(pickle.dumps(G))
     assert len(G2.simulate_walks_on_the_fly(1, 10)) == 34
+
+
+def golden_nx(name):
+    """networkx graph of a golden case, nodes inserted in the recorded list(G.nodes()) order"""
+    import networkx as nx
+    from helpers import load_case
+    z, g = load_case(name)
+    labels = z["labels"]
+    G = nx.DiGraph() if int(z["directed"]) else nx.Graph()
+    G.add_nodes_from(int(labels[i]) for i in z["order"])
+    w = z["w"]
+    for u in range(g.n):
+        for e in range(g.row_ptr[u], g.row_ptr[u + 1]):
+            wt = float(w[e])
+            G.add_edge(int(labels[u]), int(labels[g.col[e]]), weight=int(wt) if wt.is_integer() else wt)
+    return z, G
+
+
+def as_lists(z, key_w, key_l):
+    labels = z["labels"]
+    return [[int(labels[t]) for t in row[:l]] for row, l in zip(z[key_w], z[key_l])]
+
+
+def test_popularity_walks_through_public_api():
+    """main_link.simulate_walk_popularity (main_link.py:206-219) flows: popwalk 'pop' and 'both'"""
+    from node2vec_by_ecc_b200 import Graph
+    z, nxG = golden_nx("bip_pop_p1_q1")
+    G = Graph(nxG, False, float(z["p"]), float(z["q"]), "pop", seed=int(z["seed"]), mode="alias")
+    G.preprocess_transition_probs_popularity()
+    assert [list(w) for w in G.simulate_walks(int(z["R"]), int(z["L"]))] == as_lists(z, "walks", "lens")
+    G2 = Graph(nxG, False, float(z["p"]), float(z["q"]), "pop", seed=int(z["seed"]), mode="alias")
+    assert [list(w) for w in G2.simulate_walks_on_the_fly(int(z["R"]), int(z["L"]))] == as_lists(z, "walks_otf", "lens_otf")
+    # popwalk == "both": plain walks extended by popularity walks
+    G3 = Graph(nxG, False, 1.0, 1.0, "both")
+    G3.preprocess_transition_probs()
+    walks = G3.simulate_walks(1, 10)
+    G3.preprocess_transition_probs_popularity()
+    walks.extend(G3.simulate_walks(1, 10))
+    assert len(walks) == 2 * nxG.number_of_nodes()
+
+
+def test_directed_weighted_graph_through_public_api():
+    from node2vec_by_ecc_b200 import Graph
+    z, nxG = golden_nx("dir_p025_q4")
+    G = Graph(nxG, True, float(z["p"]), float(z["q"]), seed=int(z["seed"]), mode="alias")
+    G.preprocess_transition_probs()
+    assert [list(w) for w in G.simulate_walks(int(z["R"]), int(z["L"]))] == as_lists(z, "walks", "lens")
+    sub = [int(z["labels"][i]) for i in z["sub_starts"]]
+    G._walk_id_base = 1000
+    assert [list(w) for w in G.simulate_walks(2, int(z["L"]), nodes=sub)] == as_lists(z, "walks_sub", "lens_sub")
+
+
+def test_walk_file_round_trip_and_batched_link_scores(tmp_path):
+    """walk file (main_link.py:544-546) -> LineSentence (:340) -> same model; get_roc_score's cosine
+    loop (:173-189) as one n2v_cosine_pairs launch"""
+    from node2vec_by_ecc_b200 import Graph, LineSentence, Word2Vec
+    G = Graph(karate_nx(), False, 0.25, 4.0, seed=5)
+    G.preprocess_transition_probs()
+    walks = G.simulate_walks(4, 30)
+    path = tmp_path / "walks.txt"
+    walks.save_walks(str(path))
+    lines = path.read_text().splitlines()
+    assert len(lines) == len(walks) and lines[0] == " ".join(map(str, walks[0]))
+    m1 = Word2Vec([list(map(str, w)) for w in walks], size=32, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1)
+    m2 = Word2Vec(LineSentence(str(path)), size=32, window=10, min_count=0, sg=1, iter=1, hogwild_warps=1)
+    assert m1.wv.index2word == m2.wv.index2word and np.array_equal(m1.wv.syn0, m2.wv.syn0)
+    edges = [(str(a), str(b)) for a, b in list(karate_nx().edges())[:40]] + [("1", "nope"), ("nope", "2")]
+    got = m1.wv.similarity_pairs(edges)
+    want = [m1.wv.similarity(a, b) if (a in m1.wv and b in m1.wv) else 0.0 for a, b in edges]
+    assert np.abs(got - np.asarray(want, dtype=np.float32)).max() < 1e-5 and got[-1] == 0 and got[-2] == 0

@@ -32,6 +32,18 @@ def test_walks_bit_exact_vs_reference_golden(name):
     assert (walks.cpu().numpy() == z["walks_sub"]).all() and (lens.cpu().numpy() == z["lens_sub"]).all()
 
 
+def test_popularity_on_the_fly_walks_bit_exact_vs_reference_golden():
+    """popwalk="pop": simulate_walks_on_the_fly follows get_alias_nodes_cur / get_alias_edge_pop
+    (node2vec.py:13-32,:154-174) -- the golden `walks_otf` of the '9999999'-prefixed bipartite case"""
+    z, g = load_case("bip_pop_p1_q1")
+    assert not (z["walks"] == z["walks_otf"]).all()       # the two popularity laws differ (SURVEY 2, #5)
+    dg = dev_graph(g, symmetric=True, is_item=z["is_item"])
+    t = dg.build_alias_tables(float(z["p"]), float(z["q"]), popwalk=True, pop_edges=True)
+    starts = torch.as_tensor(np.tile(z["order"], int(z["R"])))
+    walks, lens = dg.walk_alias(t, starts, int(z["L"]), int(z["seed"]))
+    assert (walks.cpu().numpy() == z["walks_otf"]).all() and (lens.cpu().numpy() == z["lens_otf"]).all()
+
+
 @pytest.mark.parametrize("weighted,directed,p,q,L", [(False, False, 0.25, 4.0, 80), (True, False, 0.5, 2.0, 40),
                                                       (True, True, 4.0, 0.25, 33), (False, True, 1.0, 1.0, 7)])
 def test_walks_bit_exact_vs_oracle(weighted, directed, p, q, L):
