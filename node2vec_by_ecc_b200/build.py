@@ -37,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-Xcompiler", "-fPIC", "-fmad=true", "-I", os.path.join(ROOT, "include"),
               "-I", CSRC]
+    common += os.environ.get("N2V_NVCC_FLAGS", "").split()      # e.g. -DN2V_V3_MINB=5 (experiments)
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

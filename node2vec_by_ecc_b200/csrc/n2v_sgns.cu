@@ -548,8 +548,11 @@ sgns_train_kernel_v2(SgnsArgs a)
 // row syn0[context] moves: 1,024 B + 6,144 B / pairs-per-centre instead of 7,168 B. Distribution
 // of negatives per pair is unchanged (count^0.75); only their independence across one window is
 // given up. Negative sets with a repeated row fall back to the uncarried sequential form.
+#ifndef N2V_V3_MINB
+#define N2V_V3_MINB 4
+#endif
 template <bool ATOMIC>
-__global__ void __launch_bounds__(SGNS_BLOCK, 4)
+__global__ void __launch_bounds__(SGNS_BLOCK, N2V_V3_MINB)
 sgns_train_kernel_v3(SgnsArgs a)
 {
     constexpr int FN = 5;

@@ -126,3 +126,33 @@ def csr_torch(lo: torch.Tensor, hi: torch.Tensor, n: int):
     row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=lo.device)
     row_ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n), 0)
     return row_ptr, col
+
+
+def bipartite_edges(n_users: int = 200_000, n_items: int = 800_000, m: int = 20_000_000, seed: int = 7,
+                    device="cuda"):
+    """C3: user-item graph, user degree ~ lognormal (mean m/n_users), item choice
+    ~ Zipf(1.0), integer weights 1..5. Users are ids [0, n_users), items [n_users, n_users+n_items)
+    (the reference labels items int('9999999' + id)). -> (user int32[M], item int32[M],
+    w float64[M], n_nodes) with M <= m distinct edges."""
+    iu = torch.arange(n_users, dtype=torch.int64, device=device)
+    # lognormal(sigma=1) user activity, normalised to m edges
+    z = torch.sqrt(-2.0 * torch.log(hash_uniform(seed, 0, iu).clamp_min(1e-300))) * torch.cos(
+        2.0 * torch.pi * hash_uniform(seed, 1, iu))
+    act = torch.exp(z)
+    ucdf = torch.cumsum(act / act.sum(), 0)
+    icdf = torch.cumsum(1.0 / torch.arange(1, n_items + 1, dtype=torch.float64, device=device), 0)
+    icdf = icdf / icdf[-1]
+    keys = torch.zeros(0, dtype=torch.int64, device=device)
+    rnd = 0
+    while keys.numel() < m and rnd < 32:
+        k = int((m - keys.numel()) * 1.15) + 1024
+        idx = torch.arange(k, dtype=torch.int64, device=device) + rnd * (1 << 40)
+        u = torch.searchsorted(ucdf, hash_uniform(seed, 2, idx)).clamp_(max=n_users - 1)
+        it = torch.searchsorted(icdf, hash_uniform(seed, 3, idx)).clamp_(max=n_items - 1)
+        keys = torch.unique(torch.cat([keys, u * n_items + it]))
+        rnd += 1
+    if keys.numel() > m:
+        keys = torch.sort(keys[torch.argsort(_mix64(keys + _wrap(seed)))[:m]]).values
+    u, it = keys // n_items, keys % n_items
+    w = (1 + torch.floor(hash_uniform(seed, 4, keys) * 5.0)).to(torch.float64)
+    return u.to(torch.int32), (it + n_users).to(torch.int32), w, n_users + n_items
