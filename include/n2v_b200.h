@@ -116,14 +116,17 @@ int n2v_walk_reject(const int64_t *row_ptr, const int32_t *col, const double *w,
  *    a degree >= 2^24 or a row start >= 2^40 does not fit),
  *  - edge_hash: open-addressing set of all arcs, key = u << 32 | v, capacity = a power of two
  *    >= 2 * nnz slots of 8 bytes (n2v_edge_hash_capacity / n2v_edge_hash_build).
- * Same transition law and Philox addressing as n2v_walk_reject. */
+ * Same transition law and Philox addressing as n2v_walk_reject. strength (optional, weighted
+ * symmetric graphs): float64[N] row sums of w -- lets the return edge be folded out as an outlier
+ * for weighted graphs too (without it the dartboard is 1/p high and acceptance collapses for
+ * small p). */
 int n2v_pack_rows(const int64_t *row_ptr, int32_t n_nodes, uint64_t *packed, int *overflow_flag,
                   void *stream);
 uint64_t n2v_edge_hash_capacity(int64_t nnz);
 int n2v_edge_hash_build(const int64_t *row_ptr, const int32_t *col, int32_t n_nodes, int64_t nnz,
                         unsigned long long *table, uint64_t capacity, void *stream);
 int n2v_walk_reject_indexed(const uint64_t *packed_rows, const int32_t *col, int64_t nnz, const double *w,
-                            const n2v_slot_t *node_slots, const unsigned long long *edge_hash,
+                            const double *strength, const n2v_slot_t *node_slots, const unsigned long long *edge_hash,
                             uint64_t hash_capacity, double p, double q, int symmetric,
                             const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
                             uint64_t walk_id_base, int32_t *walks, int32_t *lens,

@@ -22,12 +22,15 @@ static inline uint32_t to_thr(double x)   // x in [0,1] -> ceil(x * 2^32) satura
 
 // alpha(prev, x) of get_alias_edge (node2vec.py:142-147): 1/p if x == prev, 1 if x is a
 // neighbour of prev, 1/q otherwise; B = dartboard height.
-static inline RejectParams make_reject_params(double p, double q, bool weighted, int symmetric)
+static inline RejectParams make_reject_params(double p, double q, bool weighted, int symmetric,
+                                              bool weighted_fold = false)
 {
     const double a_ret = 1.0 / p, a_in = 1.0, a_out = 1.0 / q;
     RejectParams rp;
     const double b_rest = a_in > a_out ? a_in : a_out;
-    rp.fold = (!weighted && symmetric && a_ret > b_rest) ? 1 : 0;
+    // the return edge can be folded out when its weight and the row's total weight are known:
+    // unit weights (K columns of area 1), or a weighted symmetric graph with strengths supplied
+    rp.fold = ((!weighted || weighted_fold) && symmetric && a_ret > b_rest) ? 1 : 0;
     rp.bound = rp.fold ? b_rest : (a_ret > b_rest ? a_ret : b_rest);
     rp.fold_mass = rp.fold ? a_ret - b_rest : 0.0;
     rp.t_ret = to_thr((rp.fold ? b_rest : a_ret) / rp.bound);

@@ -52,12 +52,13 @@ __global__ void edge_hash_build_kernel(const int64_t *__restrict__ row_ptr, cons
     }
 }
 
-enum : int { ST_ROW = 0, ST_ALIAS = 1, ST_COL = 2, ST_PROBE = 3, ST_DONE = 4 };
+enum : int { ST_ROW = 0, ST_ALIAS = 1, ST_COL = 2, ST_PROBE = 3, ST_DONE = 4, ST_STR = 5, ST_WRET = 6 };
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(W2_BLOCK)
 walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32_t *__restrict__ col,
-                           const n2v_slot_t *__restrict__ node_slots,
+                           const n2v_slot_t *__restrict__ node_slots, const double *__restrict__ w,
+                           const double *__restrict__ strength,
                            const unsigned long long *__restrict__ edge_hash, uint64_t hash_mask, RejectParams rp,
                            int64_t nnz, const int32_t *__restrict__ starts, int64_t n_walks, int32_t L, uint32_t k0,
                            uint32_t k1, uint64_t walk_id_base, int32_t *__restrict__ walks,
@@ -76,6 +77,8 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
     int64_t b = 0; int32_t K = 0;                 // row of cur
     int32_t pdeg = 0;                             // degree of prev (charged probes)
     uint32_t trial = 0, y_acc = 0, y_al = 0; int32_t x = -1; int64_t kk = 0; uint64_t slot = 0, key = 0;
+    double w_ret = 1.0, w_row = 0.0;              // weighted fold: weight of (prev,cur), total weight of cur's row
+    const bool wfold = WEIGHTED && rp.fold;
     int state = (live && L > 1) ? ST_ROW : ST_DONE;
     unsigned long long n_trials = 0, n_tests = 0, n_probes = 0;
     if (live) stage[0] = cur;
@@ -99,6 +102,8 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
         unsigned long long v = 0;
         if (state == ST_ROW) v = __ldg(reinterpret_cast<const unsigned long long *>(packed_rows + cur));
         else if (state == ST_ALIAS) v = __ldg(reinterpret_cast<const unsigned long long *>(node_slots + b + kk));
+        else if (state == ST_STR) v = __ldg(reinterpret_cast<const unsigned long long *>(strength + cur));
+        else if (state == ST_WRET) v = __ldg(reinterpret_cast<const unsigned long long *>(w + slot));
         else if (state == ST_COL) {
             const int64_t e = b + kk, e2 = e & ~1ll;
             if (e2 + 1 < nnz) v = __ldg(reinterpret_cast<const unsigned long long *>(col + e2));
@@ -106,11 +111,16 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
         } else if (state == ST_PROBE) v = __ldg(edge_hash + slot);
 
         // ---- consume
-        bool accept = false, draw = false;
+        bool accept = false, draw = false, outlier = false;
         if (state == ST_ROW) {
             b = (int64_t)(v >> PACK_DEG_BITS); K = (int32_t)(v & ((1ull << PACK_DEG_BITS) - 1));
             if (K <= 0) finish();                 // dead end (node2vec.py:76-77)
+            else if (wfold && prev >= 0) state = ST_STR;
             else { trial = 0; draw = true; }
+        } else if (state == ST_STR) {
+            w_row = __longlong_as_double((long long)v); trial = 0; draw = true;
+        } else if (state == ST_WRET) {
+            w_ret = __longlong_as_double((long long)v); state = ST_ROW;
         } else if (state == ST_ALIAS) {           // static law ~ w(cur, .): the node alias table
             if (!(y_al < (uint32_t)(v >> 32))) kk = (int64_t)(int32_t)(uint32_t)v;
             state = ST_COL;
@@ -142,15 +152,19 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
                 // outlier: the return edge carries (1/p - B') extra area on top of the B'-high
                 // dartboard of K unit-weight columns; re-drawn every trial, always accepted.
                 const double u = (double)r.w * (1.0 / 4294967296.0);
-                if (u * (rp.bound * (double)K + rp.fold_mass) < rp.fold_mass) { x = prev; accept = true; }
+                const double fm = WEIGHTED ? rp.fold_mass * w_ret : rp.fold_mass;
+                const double area = rp.bound * (WEIGHTED ? w_row : (double)K) + fm;
+                if (u * area < fm) { x = prev; accept = true; outlier = true; }
             }
-            if (trial >= 100000u && prev >= 0) { x = prev; accept = true; }   // safety valve, unreachable for sane p, q
+            if (trial >= 100000u && prev >= 0) { x = prev; accept = true; outlier = true; }   // safety valve, unreachable for sane p, q
         }
         if (accept) {
             n_trials += trial;
             prev = cur; pdeg = K; cur = x;
             emit(cur);
-            if (len >= L) finish(); else state = ST_ROW;
+            if (len >= L) finish();
+            else if (wfold && !outlier) { slot = (uint64_t)(b + kk); state = ST_WRET; }   // weight of the arc just taken
+            else state = ST_ROW;                  // (outlier: same edge walked back, w_ret unchanged)
         }
     }
     if (live) lens[i] = len;
@@ -210,7 +224,7 @@ extern "C" int n2v_edge_hash_build(const int64_t *row_ptr, const int32_t *col, i
 }
 
 extern "C" int n2v_walk_reject_indexed(const uint64_t *packed_rows, const int32_t *col, int64_t nnz, const double *w,
-                                       const n2v_slot_t *node_slots, const unsigned long long *edge_hash,
+                                       const double *strength, const n2v_slot_t *node_slots, const unsigned long long *edge_hash,
                                        uint64_t hash_capacity, double p, double q, int symmetric,
                                        const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
                                        uint64_t walk_id_base, int32_t *walks, int32_t *lens,
@@ -224,16 +238,16 @@ extern "C" int n2v_walk_reject_indexed(const uint64_t *packed_rows, const int32_
     N2V_REQUIRE(hash_capacity >= 2 && (hash_capacity & (hash_capacity - 1)) == 0, "hash capacity must be a power of two");
     N2V_REQUIRE(!w || node_slots, "weighted graph needs node_slots");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    const RejectParams rp = make_reject_params(p, q, w != nullptr, symmetric);
+    const RejectParams rp = make_reject_params(p, q, w != nullptr, symmetric, w != nullptr && strength != nullptr);
     const int64_t blocks = (n_walks + W2_BLOCK - 1) / W2_BLOCK;
     N2V_REQUIRE(blocks < 2147483647ll, "too many walks for one launch");
     if (w)
         walk_reject_indexed_kernel<true><<<(unsigned)blocks, W2_BLOCK, 0, stream>>>(
-            packed_rows, col, node_slots, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
+            packed_rows, col, node_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
             (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     else
         walk_reject_indexed_kernel<false><<<(unsigned)blocks, W2_BLOCK, 0, stream>>>(
-            packed_rows, col, node_slots, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
+            packed_rows, col, node_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
             (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     N2V_LAUNCH_CHECK();
     return N2V_OK;

@@ -232,7 +232,11 @@ class DeviceGraph:
                 table = torch.empty(cap, dtype=torch.int64, device=dev)
                 check(L.n2v_edge_hash_build(ptr(self.row_ptr), ptr(self.col), C.c_int32(self.n), C.c_int64(self.nnz),
                                             ptr(table), C.c_uint64(cap), stream()))
-                self._cache["rix"] = (packed, table, cap)
+                strength = None
+                if self.w is not None and self.symmetric:
+                    rows = torch.repeat_interleave(torch.arange(self.n, device=dev), self.row_ptr[1:] - self.row_ptr[:-1])
+                    strength = torch.zeros(max(self.n, 1), dtype=torch.float64, device=dev).index_add_(0, rows, self.w)
+                self._cache["rix"] = (packed, table, cap, strength)
         return self._cache["rix"]
 
     def walk_reject(self, p: float, q: float, starts: torch.Tensor, L_: int, seed: int,
@@ -250,9 +254,9 @@ class DeviceGraph:
             torch.empty(n, dtype=torch.int32, device=self.device))
         rix = self.reject_index() if indexed else None
         if rix is not None:
-            packed, table, cap = rix
+            packed, table, cap, strength = rix
             check(lib().n2v_walk_reject_indexed(
-                ptr(packed), ptr(self.col), C.c_int64(self.nnz), ptr(self.w),
+                ptr(packed), ptr(self.col), C.c_int64(self.nnz), ptr(self.w), ptr(strength),
                 ptr(node_tables.node_slots if node_tables is not None else None), ptr(table), C.c_uint64(cap),
                 C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts), C.c_int64(n),
                 C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base), ptr(walks), ptr(lens), ptr(counters),

@@ -127,7 +127,7 @@ def test_rejection_walker_chi_square(weighted, directed, p, q, indexed):
 def test_edge_hash_holds_exactly_the_arcs():
     _, g = random_graph(500, 6000, seed=17, directed=True, skew=0.8)
     dg = dev_graph(g, symmetric=False)
-    packed, table, cap = dg.reject_index()
+    packed, table, cap, _ = dg.reject_index()
     assert cap >= 2 * g.nnz and cap & (cap - 1) == 0
     t = table.cpu().numpy().view(np.uint64)
     keys = np.sort(t[t != np.uint64(0xFFFFFFFFFFFFFFFF)])
@@ -157,7 +157,7 @@ def test_indexed_rejection_walk_shapes_and_dead_ends(L):
             assert ln == L or deg[row[ln - 1]] == 0          # stops early only at a dead end
 
 
-@pytest.mark.parametrize("weighted,directed", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("weighted,directed", [(False, False), (False, True), (True, True)])
 def test_both_rejection_forms_make_identical_walks(weighted, directed):
     """same Philox words, same decisions: the hashed/state-machine form reproduces the
     binary-search form token by token"""
