@@ -413,7 +413,7 @@ def run_reference(a):
     syn0 = ((rng.random((voc.V, a.dim), dtype=np.float32) - 0.5) / a.dim).astype(np.float32)
     syn1 = np.zeros((voc.V, a.dim), dtype=np.float32)
     from concurrent.futures import ThreadPoolExecutor
-    nw = a.ref_walks or 4 * cores
+    nw = a.ref_walks or 32 * cores
 
     def one_step(i):
         starts = ((i * nw + np.arange(nw)) % n).astype(np.int32)
