@@ -190,6 +190,8 @@ def run_ours(a):
     kern = {"walk": [], "sgns": []}
 
     mode = {"shared": int(a.shared_negatives)}
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    pending = {"ev": None}
 
     def step(i, host_io=None, record=False):
         g0 = (i * world + rank) * B                         # global id of this rank's first walk
@@ -205,14 +207,22 @@ def run_ours(a):
             hw.copy_(walks, non_blocking=True); hl.copy_(lens, non_blocking=True)   # learn_embeddings
             walks.copy_(hw, non_blocking=True)               # takes them back in
         e2.record()
+        if pending["ev"] is not None:                        # tables of the previous step averaged?
+            torch.cuda.current_stream().wait_event(pending["ev"]); pending["ev"] = None
         trainer.train(walks, None, B, L, total_examples=total_walks, example_base=g0 % total_walks,
                       sent_id_base=g0, sent_per_job=10000 // L,
                       grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
                       atomic_updates=a.atomic, negative_sharing=mode["shared"])
         e3.record()
         if world > 1:                                        # replicated tables, averaged
-            dist.all_reduce(trainer.syn0); dist.all_reduce(trainer.syn1neg)
-            trainer.syn0.mul_(1.0 / world); trainer.syn1neg.mul_(1.0 / world)
+            # on a side stream: the all-reduce overlaps the NEXT step's walk kernel, which does not
+            # touch the tables; the next SGNS launch waits for it
+            ready = torch.cuda.Event(); ready.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_reduce(trainer.syn0); dist.all_reduce(trainer.syn1neg)
+                trainer.syn0.mul_(1.0 / world); trainer.syn1neg.mul_(1.0 / world)
+                pending["ev"] = torch.cuda.Event(); pending["ev"].record(comm)
         if host_io is not None:
             hp.copy_(trainer.pairs[:1], non_blocking=True)
             torch.cuda.current_stream().synchronize()        # the caller reads the result

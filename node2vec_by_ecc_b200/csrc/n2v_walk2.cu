@@ -54,8 +54,11 @@ __global__ void edge_hash_build_kernel(const int64_t *__restrict__ row_ptr, cons
 
 enum : int { ST_ROW = 0, ST_ALIAS = 1, ST_COL = 2, ST_PROBE = 3, ST_DONE = 4, ST_STR = 5, ST_WRET = 6 };
 
+#ifndef N2V_W2_MINB
+#define N2V_W2_MINB 5
+#endif
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(W2_BLOCK)
+__global__ void __launch_bounds__(W2_BLOCK, N2V_W2_MINB)
 walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32_t *__restrict__ col,
                            const n2v_slot_t *__restrict__ node_slots, const double *__restrict__ w,
                            const double *__restrict__ strength,
@@ -80,7 +83,7 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
     double w_ret = 1.0, w_row = 0.0;              // weighted fold: weight of (prev,cur), total weight of cur's row
     const bool wfold = WEIGHTED && rp.fold;
     int state = (live && L > 1) ? ST_ROW : ST_DONE;
-    unsigned long long n_trials = 0, n_tests = 0, n_probes = 0;
+    uint32_t n_trials = 0, n_tests = 0, n_probes = 0;   // per walker: < 2^32
     if (live) stage[0] = cur;
 
     auto emit = [&](int32_t tok) {                // append a token; one full 32-byte sector per 8 tokens
@@ -170,18 +173,19 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
     if (live) lens[i] = len;
     if (counters) {
         unsigned long long st = live && len > 0 ? (unsigned long long)(len - 1) : 0ull;
+        unsigned long long c1 = n_trials, c2 = n_tests, c3 = n_probes;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             st += __shfl_xor_sync(0xFFFFFFFFu, st, o);
-            n_trials += __shfl_xor_sync(0xFFFFFFFFu, n_trials, o);
-            n_tests += __shfl_xor_sync(0xFFFFFFFFu, n_tests, o);
-            n_probes += __shfl_xor_sync(0xFFFFFFFFu, n_probes, o);
+            c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+            c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+            c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, o);
         }
         if (lane == 0) {
             atomicAdd(counters + 0, st);
-            atomicAdd(counters + 1, n_trials);
-            atomicAdd(counters + 2, n_tests);
-            atomicAdd(counters + 3, n_probes);
+            atomicAdd(counters + 1, c1);
+            atomicAdd(counters + 2, c2);
+            atomicAdd(counters + 3, c3);
         }
     }
 }
