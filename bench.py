@@ -33,7 +33,12 @@ BYTES_PER_PAIR = 7168        # 2 x 512 B x (1 input + 1 positive +
 BYTES_PER_ALIAS_STEP = 40
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the default bench step, from the
 # committed `ncu --set full` captures (profiles/): filled in when a capture exists, else null
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {     # bytes per launch at the default workload (2^19 walks per launch)
+    "sgns_train_kernel_v3": 188.2e9,          # profiles/r01_g_sgns_v3_ncu_full.json (90.0 GB read + 98.2 GB written)
+    "sgns_train_kernel_v2": None,
+    "walk_reject_indexed_kernel": 28.44e9,    # profiles/r01_c_walk_reject_indexed_ncu_full.json
+    "walk_reject_kernel": 41.26e9,            # profiles/r01_a_walk_reject_ncu_full.json
+}
 
 
 def parse():
@@ -304,7 +309,9 @@ def run_ours(a):
             kname = "sgns_train_kernel_v2 (per-pair negatives)"
         sg_gbs = alg_bytes / (sgns_ms / 1e3) / 1e9
         roof = {"kernel": kname, "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
-                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]), "peak_source": src,
+                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]) if (a.scale == 22 and a.batch_walks == 1 << 19) else None,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)", "peak_source": src,
+                "algorithmic_bytes_per_launch": alg_bytes / a.steps,
                 "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / a.steps,
                 "centres_per_launch": centres / world / a.steps, "ms_per_launch": sgns_ms / a.steps,
                 "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (sgns_ms / 1e3) / 1e9}
@@ -317,7 +324,8 @@ def run_ours(a):
             wbytes = BYTES_PER_ALIAS_STEP * S
         w_gbs = wbytes / (walk_ms / 1e3) / 1e9
         roof_walk = {"kernel": ("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode), "bound": "hbm", "achieved": w_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_%s_kernel" % a.walk_mode),
+                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode) if (a.scale == 22 and a.batch_walks == 1 << 19) else None,
+                     "algorithmic_bytes_per_launch": wbytes / a.steps,
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}
         out = {

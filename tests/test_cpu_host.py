@@ -139,3 +139,23 @@ def test_gloo_world2_counts_and_table_averaging():
     for rank, counts, a0, a1 in res:
         assert counts == list(range(1, 11))          # disjoint shards summed
         assert a0 == 1.5 and a1 == 15.0              # (1+2)/2, (10+20)/2
+
+
+def test_bench_reference_arm_contract_small():
+    """bench.py --impl reference (the oracle port on host cores) prints ONE JSON line with the
+    contract's keys; tiny R-MAT so that it runs in seconds on CPU."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "10",
+                          "--edges", "5000", "--steps", "1", "--warmup", "0", "--ref-walks", "8"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "pairs/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]

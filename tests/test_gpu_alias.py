@@ -105,3 +105,41 @@ def test_empty_and_isolated():
     walks, lens = dg.walk_alias(t, torch.arange(5, dtype=torch.int32), 6, seed=1)
     assert (lens.cpu().numpy() == 1).all()
     assert (walks.cpu().numpy()[:, 0] == np.arange(5)).all() and (walks.cpu().numpy()[:, 1:] == -1).all()
+
+
+def test_alias_setup_many_random_vectors_vs_oracle():
+    """generated probability vectors (uniform, one-hot, zeros, heavy-tailed, sizes
+    1..3000) through ONE launch -- every row of a star-shaped CSR carries one vector, normalisation
+    off -- against oracle.alias_setup == node2vec.py:240-269. J exact, q bit-equal."""
+    from node2vec_by_ecc_b200 import DeviceGraph
+    rng = np.random.RandomState(7)
+    vecs = []
+    for K in [1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 64, 100, 257, 1000, 3000]:
+        for kind in range(5):
+            if kind == 0:
+                v = np.full(K, 1.0 / K)
+            elif kind == 1:
+                v = np.zeros(K); v[rng.randint(K)] = 1.0
+            elif kind == 2:
+                v = rng.rand(K) ** 6; v /= v.sum()
+            elif kind == 3:
+                v = rng.randint(0, 4, size=K).astype(np.float64); v = v / max(v.sum(), 1.0)   # zeros inside
+            else:
+                v = rng.dirichlet(np.full(K, 0.05))
+            vecs.append(v)
+    lens = np.asarray([len(v) for v in vecs])
+    row_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n_rows = len(vecs)
+    # rows 0..n_rows-1 carry the vectors, all pointing at leaf nodes with empty rows
+    n = n_rows + int(lens.max())
+    rp = np.concatenate([row_ptr, np.full(n - n_rows, row_ptr[-1])]).astype(np.int64)
+    col = np.concatenate([np.arange(n_rows, n_rows + k, dtype=np.int32) for k in lens])
+    dg = DeviceGraph.from_csr(rp, col, np.concatenate(vecs), symmetric=False)
+    t = dg.build_node_tables(keep_raw=True, raw_probs=True)
+    J, q = t.node_J.cpu().numpy(), t.node_q.cpu().numpy()
+    for i, v in enumerate(vecs):
+        wj, wq = oracle.alias_setup(v)
+        a, b = row_ptr[i], row_ptr[i + 1]
+        assert (J[a:b] == wj).all(), (i, len(v))
+        assert (q[a:b] == wq).all(), (i, len(v))
+    check_slots(t.node_slots[:row_ptr[-1]], J.astype(np.int64), q)
