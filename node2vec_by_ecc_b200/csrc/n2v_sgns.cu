@@ -551,7 +551,8 @@ sgns_train_kernel_v2(SgnsArgs a)
 #ifndef N2V_V3_MINB
 #define N2V_V3_MINB 4
 #endif
-template <bool ATOMIC>
+// FULL: dim == 128 exactly (every lane holds 4 floats of every row, no masking)
+template <bool ATOMIC, bool FULL>
 __global__ void __launch_bounds__(SGNS_BLOCK, N2V_V3_MINB)
 sgns_train_kernel_v3(SgnsArgs a)
 {
@@ -568,10 +569,10 @@ sgns_train_kernel_v3(SgnsArgs a)
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = a.p.grid_warps;
     if (warp >= n_warps) return;
-    const int32_t dim = a.p.dim, window = a.p.window;
+    const int32_t dim = FULL ? 128 : a.p.dim, window = a.p.window;
     const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
     const uint32_t ep8 = a.p.epoch << 8;
-    const bool on = lane * 4 < dim;
+    const bool on = FULL || (lane * 4 < dim);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float *const syn0 = a.syn0, *const syn1neg = a.syn1neg;
     unsigned long long pairs = 0, centres = 0;
@@ -640,10 +641,11 @@ sgns_train_kernel_v3(SgnsArgs a)
                     while (j < kend) {
                         const int32_t ctx = ws.idx[j];
                         int32_t jn = j + 1; if (jn == i) ++jn;
-                        // next input row in flight unless it is the row this pair is about to update
-                        const bool pre = jn < kend && ws.idx[jn] != ctx;
-                        float4 row1n = zero4;
-                        if (pre && on) row1n = ldcg4(syn0 + (int64_t)ws.idx[jn] * dim, lane);
+                        // next input row always in flight (clamped past the window's end); it is
+                        // stale only if it is the very row this pair is about to update
+                        const int32_t ctx_n = ws.idx[jn < kend ? jn : j];
+                        const bool stale = ctx_n == ctx;
+                        const float4 row1n = on ? ldcg4(syn0 + (int64_t)ctx_n * dim, lane) : zero4;
                         // 6 dot products, reduced by a transposing butterfly: after the rounds on lane
                         // bits 4,3,2 each lane holds ONE of the (padded) 8 sums, bits 1,0 finish it:
                         // 9 shuffles instead of 30, and the sigmoid is evaluated once per target
@@ -681,10 +683,11 @@ sgns_train_kernel_v3(SgnsArgs a)
                         float4 upd1 = row1;
                         upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
                         add_row<ATOMIC>(syn0 + (int64_t)ctx * dim, lane, work, upd1, on);
-                        ++pairs;
                         j = jn;
-                        if (j < kend) row1 = pre ? row1n : (on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4);
+                        row1 = row1n;
+                        if (stale && j < kend) row1 = on ? ldcg4(syn0 + (int64_t)ctx * dim, lane) : zero4;   // re-read after the update
                     }
+                    pairs += (unsigned long long)(kend - j0 - ((i >= j0 && i < kend) ? 1 : 0));
                     // one reduction per carried row: what this centre's pairs added to it
 #pragma unroll
                     for (int d = 0; d <= FN; ++d) {
@@ -840,8 +843,13 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
     if (p.negative_sharing) {
         N2V_REQUIRE(nv == 1 && p.negative == 5, "negative_sharing needs dim <= 128 and negative == 5");
         const int blocks = (p.grid_warps + SGNS_BLOCK / 32 - 1) / (SGNS_BLOCK / 32);
-        if (p.atomic_updates) sgns_train_kernel_v3<true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
-        else sgns_train_kernel_v3<false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        if (p.dim == 128) {
+            if (p.atomic_updates) sgns_train_kernel_v3<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            else sgns_train_kernel_v3<false, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        } else {
+            if (p.atomic_updates) sgns_train_kernel_v3<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            else sgns_train_kernel_v3<false, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        }
         N2V_LAUNCH_CHECK();
         return N2V_OK;
     }
