@@ -391,6 +391,11 @@ __device__ __forceinline__ float4 ldcg4(const float *row, int lane)
 {
     return __ldcg(reinterpret_cast<const float4 *>(row) + lane);
 }
+// pull a row's line(s) towards L2 without occupying registers or ordering against later accesses
+__device__ __forceinline__ void prefetch_row_l2(const float *row, int lane)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4 *>(row) + lane));
+}
 __device__ __forceinline__ float dot4(const float4 &x, const float4 &y)
 {
     return x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
@@ -638,6 +643,14 @@ sgns_train_kernel_v3(SgnsArgs a)
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
                     float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
                     const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
+                    if (ni < n_kept) {                     // next centre's output rows: L2 warm-up
+                        prefetch_row_l2(syn1neg + (int64_t)ws.idx[ni] * dim, lane);
+#pragma unroll
+                        for (int d = 0; d < FN; ++d) {
+                            const int32_t tn = __shfl_sync(0xFFFFFFFFu, t_nxt, d);
+                            if (on) prefetch_row_l2(syn1neg + (int64_t)tn * dim, lane);
+                        }
+                    }
                     while (j < kend) {
                         const int32_t ctx = ws.idx[j];
                         int32_t jn = j + 1; if (jn == i) ++jn;
@@ -646,6 +659,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                         const int32_t ctx_n = ws.idx[jn < kend ? jn : j];
                         const bool stale = ctx_n == ctx;
                         const float4 row1n = on ? ldcg4(syn0 + (int64_t)ctx_n * dim, lane) : zero4;
+
                         // 6 dot products, reduced by a transposing butterfly: after the rounds on lane
                         // bits 4,3,2 each lane holds ONE of the (padded) 8 sums, bits 1,0 finish it:
                         // 9 shuffles instead of 30, and the sigmoid is evaluated once per target
