@@ -99,6 +99,20 @@ int n2v_walk_alias(const int64_t *row_ptr, const int32_t *col, const n2v_slot_t 
                    int64_t n_walks, int32_t L, uint64_t seed, uint64_t walk_id_base,
                    int32_t *walks, int32_t *lens, void *stream);
 
+/* Second form of the alias walker, bit-identical output: every arc gets one 32-byte,
+ * sector-aligned record {edge-table offset, row start << 24 | degree of its head, head node} so
+ * that a step is two dependent sector reads (alias slot, then the chosen arc's record) instead of
+ * four to five. recs: nnz * n2v_arc_record_bytes() bytes, 32-byte aligned (n2v_pack_arcs;
+ * *overflow_flag set when a degree >= 2^24 / row start >= 2^40 does not fit); packed_rows as for
+ * n2v_walk_reject_indexed (first step). */
+size_t n2v_arc_record_bytes(void);
+int n2v_pack_arcs(const int64_t *row_ptr, const int32_t *col, const int64_t *etab_ptr, int64_t nnz,
+                  void *recs, int *overflow_flag, void *stream);
+int n2v_walk_alias_packed(const uint64_t *packed_rows, const n2v_slot_t *node_slots, const void *recs,
+                          const n2v_slot_t *edge_slots, const int32_t *starts, int64_t n_walks,
+                          int32_t L, uint64_t seed, uint64_t walk_id_base, int32_t *walks,
+                          int32_t *lens, void *stream);
+
 /* Rejection-sampling walker (KnightKing style) for graphs whose edge tables do not fit: same
  * transition distribution as get_alias_edge (node2vec.py:142-150), no edge tables.
  * node_slots may be NULL when w is NULL (uniform candidate). symmetric as above.

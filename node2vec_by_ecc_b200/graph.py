@@ -30,6 +30,8 @@ class AliasTables:
     p: float = 1.0
     q: float = 1.0
     popwalk: bool = False
+    packed_rows: torch.Tensor | None = None   # row_ptr << 24 | deg per node
+    arc_recs: torch.Tensor | None = None      # int64[nnz, 4]: one 32-byte record per arc
 
 
 @dataclass
@@ -199,17 +201,35 @@ class DeviceGraph:
                                           ptr(wJ), ptr(wq), stream()))
         if keep_raw:
             t.edge_J, t.edge_q = wJ[:total], wq[:total]
+        # packed arc records for n2v_walk_alias_packed (32 B per arc, small next to the tables)
+        L_ = lib()
+        packed = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
+        recs = torch.empty((nnz, 4), dtype=torch.int64, device=dev)          # torch allocations are 512-B aligned
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(L_.n2v_pack_rows(ptr(self.row_ptr), C.c_int32(self.n), ptr(packed), ptr(flag), stream()))
+        check(L_.n2v_pack_arcs(ptr(self.row_ptr), ptr(self.col), ptr(etab), C.c_int64(nnz), ptr(recs), ptr(flag),
+                               stream()))
+        if int(flag.item()) == 0:
+            t.packed_rows, t.arc_recs = packed, recs
         return t
 
     # ---- walks ------------------------------------------------------------------------------------
     def walk_alias(self, tables: AliasTables, starts: torch.Tensor, L_: int, seed: int,
-                   walk_id_base: int = 0, out=None):
-        """simulate_walks (node2vec.py:81-95): -> (walks int32[n, L] padded -1, lens int32[n])."""
+                   walk_id_base: int = 0, out=None, packed: bool = True):
+        """simulate_walks (node2vec.py:81-95): -> (walks int32[n, L] padded -1, lens int32[n]).
+        packed=True walks over the 32-byte arc records (n2v_walk_alias_packed) when the tables carry
+        them, False over row_ptr / etab_ptr / col (n2v_walk_alias); the output is identical."""
         starts = torch.as_tensor(starts, dtype=torch.int32).to(self.device).contiguous()
         n = int(starts.shape[0])
         walks, lens = out if out is not None else (
             torch.empty((n, L_), dtype=torch.int32, device=self.device),
             torch.empty(n, dtype=torch.int32, device=self.device))
+        if packed and tables.arc_recs is not None:
+            check(lib().n2v_walk_alias_packed(ptr(tables.packed_rows), ptr(tables.node_slots), ptr(tables.arc_recs),
+                                              ptr(tables.edge_slots), ptr(starts), C.c_int64(n), C.c_int32(L_),
+                                              C.c_uint64(seed), C.c_uint64(walk_id_base), ptr(walks), ptr(lens),
+                                              stream()))
+            return walks, lens
         check(lib().n2v_walk_alias(ptr(self.row_ptr), ptr(self.col), ptr(tables.node_slots),
                                    ptr(tables.etab_ptr), ptr(tables.edge_slots), ptr(starts), C.c_int64(n),
                                    C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base), ptr(walks),

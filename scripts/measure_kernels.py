@@ -56,11 +56,13 @@ def alias_case(name, lo, hi, n, p, q, R, L):
     starts = torch.arange(n, dtype=torch.int32, device=dev).repeat(R)
     walks = torch.empty((starts.shape[0], L), dtype=torch.int32, device=dev)
     lens = torch.empty(starts.shape[0], dtype=torch.int32, device=dev)
+    ms_unpacked = timeit(lambda: dg.walk_alias(t, starts, L, 1, 0, out=(walks, lens), packed=False))
     ms = timeit(lambda: dg.walk_alias(t, starts, L, 1, 0, out=(walks, lens)))
     steps = int((lens.to(torch.int64) - 1).sum().item())
     emit(what="alias build + alias walk", graph=name, n=n, nnz=dg.nnz, edge_table_entries=tot, p=p, q=q,
          build_s=build_s, entries_per_s=(tot + dg.nnz) / build_s, slot_GBps=(tot + dg.nnz) * 8 / build_s / 1e9,
          walks=int(starts.shape[0]), L=L, walk_ms=ms, steps_per_s=steps / ms * 1e3,
+         steps_per_s_unpacked_form=steps / ms_unpacked * 1e3,
          GBps_at_40B_per_step=steps * 40 / ms / 1e6, frac_of_stream_peak=steps * 40 / ms / 1e6 / PEAK)
     cnt = torch.zeros(4, dtype=torch.int64, device=dev)
     ms = timeit(lambda: dg.walk_reject(p, q, starts, L, 1, 0, counters=cnt, out=(walks, lens)))

@@ -23,9 +23,10 @@ def test_walks_bit_exact_vs_reference_golden(name):
     dg = dev_graph(g, symmetric=not bool(int(z["directed"])), is_item=z["is_item"])
     t = dg.build_alias_tables(float(z["p"]), float(z["q"]), popwalk=bool(int(z["popwalk"])))
     starts = torch.as_tensor(np.tile(z["order"], int(z["R"])))
-    walks, lens = dg.walk_alias(t, starts, L, seed)
-    assert (lens.cpu().numpy() == z["lens"]).all()
-    assert (walks.cpu().numpy() == z["walks"]).all()
+    for packed in (True, False):
+        walks, lens = dg.walk_alias(t, starts, L, seed, packed=packed)
+        assert (lens.cpu().numpy() == z["lens"]).all()
+        assert (walks.cpu().numpy() == z["walks"]).all()
     # a contiguous shard of start nodes with a walk-id base (main_link.py:263-264 partitioning)
     sub = torch.as_tensor(np.tile(z["sub_starts"], 2))
     walks, lens = dg.walk_alias(t, sub, L, seed, walk_id_base=1000)
@@ -53,9 +54,11 @@ def test_walks_bit_exact_vs_oracle(weighted, directed, p, q, L):
     want, want_len = oracle.walks_alias(g, to, starts, L, seed=77, walk_id_base=5)
     dg = dev_graph(g, symmetric=not directed)
     t = dg.build_alias_tables(p, q)
-    walks, lens = dg.walk_alias(t, torch.as_tensor(starts), L, seed=77, walk_id_base=5)
-    assert (lens.cpu().numpy() == want_len).all()
-    assert (walks.cpu().numpy() == want).all()
+    assert t.arc_recs is not None
+    for packed in (True, False):                      # both alias walkers: same tokens
+        walks, lens = dg.walk_alias(t, torch.as_tensor(starts), L, seed=77, walk_id_base=5, packed=packed)
+        assert (lens.cpu().numpy() == want_len).all()
+        assert (walks.cpu().numpy() == want).all()
     if directed:
         assert (want_len < L).any()          # dead ends exercised
 
