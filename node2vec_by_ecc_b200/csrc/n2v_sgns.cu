@@ -280,12 +280,12 @@ __device__ __forceinline__ float job_alpha(const n2v_sgns_params_t &p, int64_t s
 }
 
 // train_batch_sg prologue: sub-sample + per-position window shrink, compacted in sentence order.
-// Fills the staging arrays from tokens [t_next, tl) until the chunk is full; returns n_kept.
+// Appends to the n_kept tokens already staged from tokens [t_next, tl) until the buffer is full;
+// returns the new n_kept.
 __device__ __forceinline__ int32_t load_chunk(const SgnsArgs &a, const WarpSentence &ws, int64_t tb, int64_t tl,
                                               int64_t &t_next, uint64_t gs, uint32_t ep8, uint32_t k0,
-                                              uint32_t k1, int lane)
+                                              uint32_t k1, int lane, int32_t n_kept)
 {
-    int32_t n_kept = 0;
     while (t_next < tl && n_kept <= SGNS_SMEM_TOKENS - 32) {
         const int64_t t = t_next + lane;
         int32_t wv = -1; uint32_t red = 0;
@@ -308,6 +308,34 @@ __device__ __forceinline__ int32_t load_chunk(const SgnsArgs &a, const WarpSente
     }
     __syncwarp();
     return n_kept;
+}
+
+// Streams a sentence of any length (<= max_sentence_len) through the per-warp staging buffer with
+// exact windows: centres [c_lo, c_hi) of the buffer are the ones whose full window is present;
+// between chunks the last 2*window kept tokens are carried over (window of left context + the
+// window of centres that still lacked their right context). Returns false when the sentence is done.
+__device__ __forceinline__ bool next_chunk(const SgnsArgs &a, const WarpSentence &ws, int64_t tb, int64_t tl,
+                                           int64_t &t_next, uint64_t gs, uint32_t ep8, uint32_t k0, uint32_t k1,
+                                           int lane, int32_t &n_kept, int32_t &c_lo, int32_t &c_hi, bool &first)
+{
+    const int32_t window = a.p.window;
+    if (first) { first = false; n_kept = 0; c_lo = 0; }
+    else {
+        if (t_next >= tl) return false;                     // the previous chunk was the last one
+        const int32_t src = c_hi - window, keep = n_kept - src;   // = 2 * window
+        for (int32_t c = 0; c < keep; c += 32) {
+            const int32_t k = c + lane;
+            int32_t vi = 0; uint16_t vp = 0; uint8_t vr = 0;
+            if (k < keep) { vi = ws.idx[src + k]; vp = ws.pos[src + k]; vr = ws.rw[src + k]; }
+            __syncwarp();
+            if (k < keep) { ws.idx[k] = vi; ws.pos[k] = vp; ws.rw[k] = vr; }
+            __syncwarp();
+        }
+        n_kept = keep; c_lo = window;
+    }
+    n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept);
+    c_hi = (t_next >= tl) ? n_kept : n_kept - window;
+    return true;
 }
 
 // lane n (< negative) draws negative n of pair (i, j)
@@ -358,11 +386,11 @@ sgns_train_kernel(SgnsArgs a)
         if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
         const float alpha = job_alpha(a.p, s);
-        // Sentences longer than the staging buffer are processed in chunks of kept tokens.
         int64_t t_next = 0;
-        while (t_next < tl) {
-            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
-            for (int32_t i = 0; i < n_kept; ++i) {
+        int32_t n_kept = 0, c_lo = 0, c_hi = 0;
+        bool first_chunk = true;
+        while (next_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept, c_lo, c_hi, first_chunk)) {
+            for (int32_t i = c_lo; i < c_hi; ++i) {
                 const int32_t centre = ws.idx[i];
                 int32_t j = i - window + ws.rw[i]; if (j < 0) j = 0;
                 int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
@@ -444,15 +472,16 @@ sgns_train_kernel_v2(SgnsArgs a)
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
         const float alpha = job_alpha(a.p, s);
         int64_t t_next = 0;
-        while (t_next < tl) {
-            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
+        int32_t n_kept = 0, c_lo = 0, c_hi = 0;
+        bool first_chunk = true;
+        while (next_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept, c_lo, c_hi, first_chunk)) {
             // pair cursor (i, j) in gensim's order: centres ascending, contexts ascending, j != i
-            int32_t i = -1, j = 0, kend = 0;
+            int32_t i = c_lo - 1, j = 0, kend = 0;
             auto seek = [&]() -> bool {
                 for (;;) {
-                    if (i >= n_kept) return false;
+                    if (i >= c_hi) return false;
                     if (j < kend) { if (j != i) return true; ++j; continue; }
-                    if (++i >= n_kept) return false;
+                    if (++i >= c_hi) return false;
                     j = i - window + ws.rw[i]; if (j < 0) j = 0;
                     kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 }
@@ -604,18 +633,19 @@ sgns_train_kernel_v3(SgnsArgs a)
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
         const float alpha = job_alpha(a.p, s);
         int64_t t_next = 0;
-        while (t_next < tl) {
-            const int32_t n_kept = load_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane);
+        int32_t n_kept = 0, c_lo = 0, c_hi = 0;
+        bool first_chunk = true;
+        while (next_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept, c_lo, c_hi, first_chunk)) {
             // centres that have at least one context pair, in order; negatives drawn one centre ahead
             auto bounds = [&](int32_t i, int32_t &j0, int32_t &kend) -> bool {
                 j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
                 kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 return (kend - j0) > ((i >= j0 && i < kend) ? 1 : 0);
             };
-            int32_t i = 0, j0 = 0, kend = 0;
-            while (i < n_kept && !bounds(i, j0, kend)) ++i;
-            int32_t t_cur = i < n_kept ? draw_centre(i, gs) : -1;
-            while (i < n_kept) {
+            int32_t i = c_lo, j0 = 0, kend = 0;
+            while (i < c_hi && !bounds(i, j0, kend)) ++i;
+            int32_t t_cur = i < c_hi ? draw_centre(i, gs) : -1;
+            while (i < c_hi) {
                 const int32_t centre = ws.idx[i];
                 ++centres;
                 int32_t tg[FN];
@@ -628,7 +658,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                     for (int d2 = d1 + 1; d2 < FN; ++d2) dup |= (tg[d1] == tg[d2]) && (tg[d1] != centre);
                 // next centre with pairs + its negatives (off the critical path)
                 int32_t ni = i + 1, nj0 = 0, nkend = 0;
-                while (ni < n_kept && !bounds(ni, nj0, nkend)) ++ni;
+                while (ni < c_hi && !bounds(ni, nj0, nkend)) ++ni;
                 if (!dup) {
                     float4 out[FN + 1], orig[FN + 1];
                     uint32_t skipmask = 0xC0u;                 // padding targets 6, 7
@@ -642,8 +672,8 @@ sgns_train_kernel_v3(SgnsArgs a)
                     for (int d = 0; d <= FN; ++d) orig[d] = out[d];
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
                     float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
-                    const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
-                    if (ni < n_kept) {                     // next centre's output rows: L2 warm-up
+                    const int32_t t_nxt = ni < c_hi ? draw_centre(ni, gs) : -1;
+                    if (ni < c_hi) {                       // next centre's output rows: L2 warm-up
                         prefetch_row_l2(syn1neg + (int64_t)ws.idx[ni] * dim, lane);
 #pragma unroll
                         for (int d = 0; d < FN; ++d) {
@@ -713,7 +743,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                     t_cur = t_nxt;
                 } else {
                     // repeated row in the set: uncarried sequential form (every target re-read per pair)
-                    const int32_t t_nxt = ni < n_kept ? draw_centre(ni, gs) : -1;
+                    const int32_t t_nxt = ni < c_hi ? draw_centre(ni, gs) : -1;
                     const bool act1[1] = {on};
                     for (int32_t j = j0; j < kend; ++j) {
                         if (j == i) continue;
@@ -843,7 +873,7 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
     N2V_REQUIRE(tokens && cum_table && bucket_lo && syn0 && syn1neg, "NULL buffer");
     N2V_REQUIRE(sent_off || stride > 0, "need sent_off or a positive stride");
     N2V_REQUIRE(p.V > 0 && p.dim > 0 && p.dim % 4 == 0 && p.dim <= 1024, "dim must be a multiple of 4, <= 1024");
-    N2V_REQUIRE(p.window >= 1 && p.window <= 255, "window out of range");
+    N2V_REQUIRE(p.window >= 1 && p.window <= 96, "window out of range (1..96)");
     N2V_REQUIRE(p.negative >= 0 && p.negative <= SGNS_MAX_NEG, "negative out of range");
     N2V_REQUIRE(p.max_sentence_len >= 1 && p.max_sentence_len <= 65535, "max_sentence_len out of range");
     N2V_REQUIRE(p.grid_warps >= 1 && p.total_examples >= 1 && p.sent_per_job >= 1, "bad schedule");

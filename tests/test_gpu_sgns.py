@@ -198,3 +198,27 @@ def test_hogwild_auc_matches_oracle(shared):
     print('AUC device', auc_dev, 'oracle', auc_ref)
     assert np.mean(auc_ref) > 0.6, (auc_dev, auc_ref)   # the protocol is learning something
     assert abs(np.mean(auc_dev) - np.mean(auc_ref)) <= 0.005, (auc_dev, auc_ref)
+
+
+@pytest.mark.parametrize("shared,negative", [(1, 5), (0, 5), (0, 3)])
+def test_long_ragged_sentences_stream_with_exact_windows(shared, negative):
+    """Sentences longer than the 256-token per-warp staging buffer are streamed with a carry-over
+    of 2*window kept tokens: windows never break at a chunk boundary. Ragged corpus (0..1000
+    tokens per sentence) through the generic string path, all three kernels, vs the oracle."""
+    from node2vec_by_ecc_b200 import Word2Vec
+    rng = np.random.RandomState(5)
+    lens = [1000, 224, 225, 257, 3, 1, 0, 500, 300]
+    sents = [[str(t) for t in rng.randint(0, 60, size=n)] for n in lens]
+    m = Word2Vec(sents, size=32, window=10, min_count=0, sg=1, iter=1, negative=negative, sample=1e-2,
+                 seed=2, hogwild_warps=1, shared_negatives=shared)
+    tok = np.asarray([m.wv.vocab[w].index for s in sents for w in s], dtype=np.int32)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    counts = np.asarray([m.wv.vocab[w].count for w in m.wv.index2word], dtype=np.int64)
+    keep = m._keep_thr.cpu().numpy().view(np.uint32).astype(np.uint64)
+    keep = np.where(keep == 0xFFFFFFFF, np.uint64(1) << np.uint64(32), keep)
+    voc = oracle.Vocab(counts, np.arange(len(counts), dtype=np.int32), np.arange(len(counts), dtype=np.int32),
+                       keep, m._cum_table.cpu().numpy().view(np.uint32).copy())
+    s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=32, window=10, negative=negative, iters=1, workers=1,
+                                      rng_mode=3 if shared else 1, seed=2)
+    assert m.pairs_trained == pairs and pairs > 20000
+    assert np.abs(m.wv.syn0 - s0).max() < 2e-4 and np.abs(m.syn1neg_dev.cpu().numpy() - s1).max() < 2e-4
