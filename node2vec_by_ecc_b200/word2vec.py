@@ -116,6 +116,57 @@ class KeyedVectors:
                                      ptr(out), stream()))
         return out.cpu().numpy()
 
+    def top_k_links(self, words_a, words_b=None, k=10, exclude=(), block_rows=4096):
+        """All-pairs link scoring of link_prediction / make_links_and_score / links_score
+        (main_link.py:69-171): cosine of every candidate pair -- words_a x words_b ("separated"
+        user x item mode) or, with words_b None, every unordered pair i < j of words_a -- minus the
+        `exclude` pairs (train edges, either orientation), global top-k by score.
+        -> list of ((a, b), score), best first. One [block, d] x [d, |B|] cuBLAS SGEMM per block of
+        rows (the one dense-GEMM spot of the path) + a running top-k on the device."""
+        dev = require_cuda()
+        words_a = list(words_a)
+        same = words_b is None
+        words_b = words_a if same else list(words_b)
+        emb = (self._syn0_dev if self._syn0_dev is not None else torch.as_tensor(self._syn0_host).to(dev)).float()
+        emb = emb / emb.norm(dim=1, keepdim=True).clamp_min(1e-30)
+        ia = torch.as_tensor([self.vocab[w].index for w in words_a], device=dev)
+        ib = torch.as_tensor([self.vocab[w].index for w in words_b], device=dev)
+        A, Bm = emb[ia], emb[ib]
+        pos_a = {w: i for i, w in enumerate(words_a)}
+        pos_b = pos_a if same else {w: i for i, w in enumerate(words_b)}
+        ex = []
+        for a, b in exclude:
+            if a in pos_a and b in pos_b:
+                ex.append((pos_a[a], pos_b[b]))
+            if b in pos_a and a in pos_b:
+                ex.append((pos_a[b], pos_b[a]))
+        ex = torch.as_tensor(ex, dtype=torch.int64, device=dev).reshape(-1, 2)
+        best_s = torch.full((0,), 0.0, device=dev)
+        best_i = torch.zeros((0,), dtype=torch.int64, device=dev)
+        nb = len(words_b)
+        for r0 in range(0, len(words_a), block_rows):
+            r1 = min(len(words_a), r0 + block_rows)
+            S = A[r0:r1] @ Bm.T
+            if same:                                   # pairs i < j only (main_link.py:72)
+                rows = torch.arange(r0, r1, device=dev)[:, None]
+                S.masked_fill_(torch.arange(nb, device=dev)[None, :] <= rows, float("-inf"))
+            if ex.numel():
+                m = (ex[:, 0] >= r0) & (ex[:, 0] < r1)
+                S[ex[m, 0] - r0, ex[m, 1]] = float("-inf")
+            kk = min(k, S.numel())
+            s, i = torch.topk(S.reshape(-1), kk)
+            best_s = torch.cat([best_s, s]); best_i = torch.cat([best_i, i + r0 * nb])
+            if best_s.numel() > k:
+                s, o = torch.topk(best_s, k)
+                best_s, best_i = s, best_i[o]
+        keep = torch.isfinite(best_s)
+        best_s, best_i = best_s[keep], best_i[keep]
+        order = torch.argsort(best_s, descending=True, stable=True)
+        out = []
+        for s, i in zip(best_s[order].tolist(), best_i[order].tolist()):
+            out.append(((words_a[i // nb], words_b[i % nb]), s))
+        return out
+
     def most_similar(self, positive, topn=10):
         if isinstance(positive, (str, bytes)):
             positive = [positive]

@@ -149,3 +149,37 @@ def test_walk_file_round_trip_and_batched_link_scores(tmp_path):
     got = m1.wv.similarity_pairs(edges)
     want = [m1.wv.similarity(a, b) if (a in m1.wv and b in m1.wv) else 0.0 for a, b in edges]
     assert np.abs(got - np.asarray(want, dtype=np.float32)).max() < 1e-5 and got[-1] == 0 and got[-2] == 0
+
+
+def test_all_pairs_top_k_links_matches_brute_force():
+    """link_prediction's all-pairs scoring (main_link.py:69-171) on the device vs numpy"""
+    from node2vec_by_ecc_b200 import KeyedVectors, Vocab
+    rng = np.random.RandomState(0)
+    V, d = 300, 128
+    kv = KeyedVectors(d)
+    kv.index2word = [str(i) for i in range(V)]
+    kv.vocab = {w: Vocab(i, 1) for i, w in enumerate(kv.index2word)}
+    kv.syn0 = rng.randn(V, d).astype(np.float32)
+    e = kv.syn0 / np.linalg.norm(kv.syn0, axis=1, keepdims=True)
+    users = [str(i) for i in range(0, 120)]
+    items = [str(i) for i in range(120, 300)]
+    train = [(str(rng.randint(0, 120)), str(rng.randint(120, 300))) for _ in range(500)]
+    train += [(b, a) for a, b in train[:50]]                   # either orientation is excluded
+    got = kv.top_k_links(users, items, k=50, exclude=train, block_rows=37)
+    S = e[:120] @ e[120:].T
+    for a, b in train:
+        if int(a) >= 120:
+            a, b = b, a
+        S[int(a), int(b) - 120] = -np.inf
+    flat = np.argsort(-S.ravel(), kind="stable")[:50]
+    want = [(str(i // 180), str(120 + i % 180)) for i in flat]
+    assert [p for p, _ in got] == want
+    assert np.allclose([s for _, s in got], S.ravel()[flat], atol=1e-5)
+    # unseparated mode: unordered pairs i < j of one node list
+    nodes = [str(i) for i in range(200)]
+    got = kv.top_k_links(nodes, None, k=30, exclude=[("3", "7")], block_rows=64)
+    S = e[:200] @ e[:200].T
+    S[np.tril_indices(200)] = -np.inf
+    S[3, 7] = -np.inf
+    flat = np.argsort(-S.ravel(), kind="stable")[:30]
+    assert [p for p, _ in got] == [(str(i // 200), str(i % 200)) for i in flat]
