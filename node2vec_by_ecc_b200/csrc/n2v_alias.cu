@@ -56,6 +56,7 @@ __device__ __forceinline__ void finish_table(int64_t K, double *wq, int32_t *wJ,
     // D: while len(smaller) > 0 and len(larger) > 0 (:259-268)
     if (lane == 0) {
         int64_t si = K - 1, li = K - 1, pending = -1, cur_large = -1;
+        double q_large = 0.0;                      // q of the current large lives in a register
         for (;;) {
             int64_t small;
             if (pending >= 0) small = pending;
@@ -68,13 +69,17 @@ __device__ __forceinline__ void finish_table(int64_t K, double *wq, int32_t *wJ,
                 while (li >= 0 && wJ[li] != MARK_LARGE) --li;
                 if (li < 0) break;
                 cur_large = li--;
+                q_large = wq[cur_large];
             }
             if (pending >= 0) pending = -1; else --si;
             wJ[small] = (int32_t)cur_large;                                   // J[small] = large
-            double ql = __dadd_rn(__dadd_rn(wq[cur_large], wq[small]), -1.0); // q[large]+q[small]-1.0
-            wq[cur_large] = ql;
-            if (ql < 1.0) { wJ[cur_large] = MARK_DEMOTED; pending = cur_large; cur_large = -1; }
+            q_large = __dadd_rn(__dadd_rn(q_large, wq[small]), -1.0);         // q[large]+q[small]-1.0
+            if (q_large < 1.0) {
+                wq[cur_large] = q_large; wJ[cur_large] = MARK_DEMOTED;
+                pending = cur_large; cur_large = -1;
+            }
         }
+        if (cur_large >= 0) wq[cur_large] = q_large;
     }
     __syncwarp();
     // E: leftovers keep J = 0 (np.zeros, :248); pack
