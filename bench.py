@@ -34,9 +34,9 @@ BYTES_PER_ALIAS_STEP = 40
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the default bench step, from the
 # committed `ncu --set full` captures (profiles/): filled in when a capture exists, else null
 NCU_TRAFFIC = {     # bytes per launch at the default workload (2^19 walks per launch)
-    "sgns_train_kernel_v3": 188.2e9,          # profiles/r01_g_sgns_v3_ncu_full.json (90.0 GB read + 98.2 GB written)
+    "sgns_train_kernel_v3": 189.8e9,          # profiles/r01_j_sgns_v3_ncu_full.json (91.6 GB read + 98.2 GB written)
     "sgns_train_kernel_v2": None,
-    "walk_reject_indexed_kernel": 28.44e9,    # profiles/r01_c_walk_reject_indexed_ncu_full.json
+    "walk_reject_indexed_kernel": 28.43e9,    # profiles/r01_j_walk_reject_indexed_ncu_full.json
     "walk_reject_kernel": 41.26e9,            # profiles/r01_a_walk_reject_ncu_full.json
 }
 
