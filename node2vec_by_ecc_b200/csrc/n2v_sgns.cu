@@ -583,7 +583,7 @@ sgns_train_kernel_v2(SgnsArgs a)
 // of negatives per pair is unchanged (count^0.75); only their independence across one window is
 // given up. Negative sets with a repeated row fall back to the uncarried sequential form.
 #ifndef N2V_V3_MINB
-#define N2V_V3_MINB 4
+#define N2V_V3_MINB 5
 #endif
 // FULL: dim == 128 exactly (every lane holds 4 floats of every row, no masking)
 template <bool ATOMIC, bool FULL>
@@ -595,6 +595,9 @@ sgns_train_kernel_v3(SgnsArgs a)
     __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ float s_exp[EXP_TABLE_SIZE];
+    // the carried rows as first read (one reduction of out - orig per row at the end of a centre):
+    // parked in shared memory, each lane touches only its own 16 bytes -- keeps 24 registers free
+    __shared__ float4 s_orig[SGNS_BLOCK / 32][FN + 1][32];
     for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
     __syncthreads();
 
@@ -660,7 +663,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                 int32_t ni = i + 1, nj0 = 0, nkend = 0;
                 while (ni < c_hi && !bounds(ni, nj0, nkend)) ++ni;
                 if (!dup) {
-                    float4 out[FN + 1], orig[FN + 1];
+                    float4 out[FN + 1];
                     uint32_t skipmask = 0xC0u;                 // padding targets 6, 7
                     out[0] = on ? ldcg4(syn1neg + (int64_t)centre * dim, lane) : zero4;
 #pragma unroll
@@ -669,7 +672,7 @@ sgns_train_kernel_v3(SgnsArgs a)
 #pragma unroll
                     for (int d = 0; d < FN; ++d) if (tg[d] == centre) skipmask |= 2u << d;   // skipped, not redrawn
 #pragma unroll
-                    for (int d = 0; d <= FN; ++d) orig[d] = out[d];
+                    for (int d = 0; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
                     float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
                     const int32_t t_nxt = ni < c_hi ? draw_centre(ni, gs) : -1;
@@ -736,8 +739,8 @@ sgns_train_kernel_v3(SgnsArgs a)
 #pragma unroll
                     for (int d = 0; d <= FN; ++d) {
                         if ((skipmask >> d) & 1u) continue;
-                        const float4 dl = make_float4(out[d].x - orig[d].x, out[d].y - orig[d].y,
-                                                      out[d].z - orig[d].z, out[d].w - orig[d].w);
+                        const float4 og = s_orig[wib][d][lane];
+                        const float4 dl = make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w);
                         add_row<ATOMIC>(syn1neg + (int64_t)(d == 0 ? centre : tg[d - 1]) * dim, lane, dl, out[d], on);
                     }
                     t_cur = t_nxt;

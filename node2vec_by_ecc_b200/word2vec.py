@@ -240,7 +240,7 @@ class SgnsTrainer:
         V/4 for small vocabularies (scripts/auc_sweep.py: |dAUC| <= 0.003 up to V/2 with atomic
         updates) and at the machine width (24 resident warps per SM) otherwise."""
         sms = int(lib().n2v_sm_count())
-        return int(max(4, min(sms * (16 if shared else 24), self.V // 4)))
+        return int(max(4, min(sms * (20 if shared else 24), self.V // 4)))
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
               epoch=0, sent_per_job=125, grid_warps=None, atomic_updates=1, alpha=None, min_alpha=None,
