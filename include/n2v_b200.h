@@ -208,6 +208,20 @@ int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sen
 int n2v_cosine_pairs(const float *emb, int32_t dim, const int32_t *a, const int32_t *b,
                      int64_t n_pairs, float *out, void *stream);
 
+/* ---- walk-file formatter ---------------------------------------------------------------------
+ * replaces: " ".join(map(str, walk)) per line of the walk file (src/main_link.py:237-239,:544-546)
+ * that LineSentence (:340) reads back. Two steps because the byte count is data dependent:
+ *  1. n2v_format_walks_offsets: tok_off int64[n_walks*L + 1] = byte offset of every token slot
+ *     (tok_off[n_walks*L] = total bytes); labels int64[N] = label of compact id, or NULL = ids;
+ *  2. n2v_format_walks_write into out[total bytes]. */
+size_t n2v_format_workspace_bytes(int64_t n_walks, int32_t L);
+int n2v_format_walks_offsets(const int32_t *walks, const int32_t *lens, int64_t n_walks, int32_t L,
+                             const int64_t *labels, int64_t *tok_off, void *workspace,
+                             size_t workspace_bytes, void *stream);
+int n2v_format_walks_write(const int32_t *walks, const int32_t *lens, int64_t n_walks, int32_t L,
+                           const int64_t *labels, const int64_t *tok_off, unsigned char *out,
+                           void *stream);
+
 /* ---- measurement helpers -------------------------------------------------------------------
  * Random-access HBM roofline denominators: mode 0 = one random 32-byte sector
  * read per access; mode 1 = random 512-byte row read-modify-write. buf holds n_bytes;

@@ -56,19 +56,47 @@ class WalkCorpus(Sequence):
         out.extend(other)
         return out
 
-    def save_walks(self, path, mode="w"):
+    def format_walks(self, first=0, last=None) -> torch.Tensor:
+        """Walks [first, last) as the bytes of the walk file (uint8 device tensor), formatted on the
+        device (n2v_format_walks_*); integer labels only."""
+        import ctypes as C
+        from ._lib import check, lib, ptr, stream
+        last = len(self) if last is None else last
+        w, l = self.walks[first:last].contiguous(), self.lens[first:last].contiguous()
+        n, L = int(w.shape[0]), int(w.shape[1])
+        dev = w.device
+        lab = None
+        if self.labels is not None:
+            if self.labels.dtype == object or not np.issubdtype(self.labels.dtype, np.integer):
+                raise TypeError("device formatting needs integer node labels")
+            lab = torch.as_tensor(self.labels.astype(np.int64)).to(dev)
+        Lb = lib()
+        ws_bytes = int(Lb.n2v_format_workspace_bytes(C.c_int64(n), C.c_int32(L)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        off = torch.empty(n * L + 1, dtype=torch.int64, device=dev)
+        check(Lb.n2v_format_walks_offsets(ptr(w), ptr(l), C.c_int64(n), C.c_int32(L), ptr(lab), ptr(off), ptr(ws),
+                                          C.c_size_t(ws_bytes), stream()))
+        total = int(off[-1].item())
+        out = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+        check(Lb.n2v_format_walks_write(ptr(w), ptr(l), C.c_int64(n), C.c_int32(L), ptr(lab), ptr(off), ptr(out),
+                                        stream()))
+        return out[:total]
+
+    def save_walks(self, path, mode="w", chunk_walks=1 << 22):
         """The walk file of main_link.py:237-239,544-546: one walk per line, tokens (original
-        labels) joined by single spaces -- what LineSentence / `-walk-path` read back."""
-        w, l = self._h()
+        labels) joined by single spaces -- what LineSentence / `-walk-path` read back. Integer
+        labels are formatted on the device in chunks of `chunk_walks`; other labels on the host."""
         lab = self.labels
+        if self.walks.is_cuda and (lab is None or (lab.dtype != object and np.issubdtype(lab.dtype, np.integer))):
+            with open(path, mode + "b") as f:
+                for a in range(0, len(self), chunk_walks):
+                    f.write(self.format_walks(a, min(len(self), a + chunk_walks)).cpu().numpy().tobytes())
+            return
+        w, l = self._h()
         with open(path, mode) as f:
-            full = l == w.shape[1]
-            if lab is not None and lab.dtype != object and np.issubdtype(lab.dtype, np.integer) and full.all():
-                np.savetxt(f, lab[w], fmt="%d", delimiter=" ")
-            else:
-                for i in range(w.shape[0]):
-                    row = w[i, :l[i]]
-                    f.write(" ".join(map(str, row.tolist() if lab is None else lab[row].tolist())) + "\n")
+            for i in range(w.shape[0]):
+                row = w[i, :l[i]]
+                f.write(" ".join(map(str, row.tolist() if lab is None else lab[row].tolist())) + "\n")
 
     # -- list-of-lists view
     def _h(self):

@@ -183,3 +183,28 @@ def test_all_pairs_top_k_links_matches_brute_force():
     S[3, 7] = -np.inf
     flat = np.argsort(-S.ravel(), kind="stable")[:30]
     assert [p for p, _ in got] == [(str(i // 200), str(i % 200)) for i in flat]
+
+
+def test_device_walk_formatter_matches_python_join(tmp_path):
+    """n2v_format_walks_* == " ".join(map(str, walk)) per line (main_link.py:544-546): ragged walks,
+    negative and 19-digit labels, the '9999999' item prefix, several chunks"""
+    import torch
+    from node2vec_by_ecc_b200 import WalkCorpus
+    rng = np.random.RandomState(1)
+    labels = np.concatenate([[0, -7, 9, 10, 99, 100, 2 ** 62, -2 ** 62, 99999991, 999999912345],
+                             rng.randint(0, 10 ** 9, size=90)]).astype(np.int64)
+    n, L = 1000, 17
+    walks = rng.randint(0, len(labels), size=(n, L)).astype(np.int32)
+    lens = rng.randint(1, L + 1, size=n).astype(np.int32)
+    lens[:5] = [L, 1, 2, L, 1]
+    for i in range(n):
+        walks[i, lens[i]:] = -1
+    c = WalkCorpus(torch.as_tensor(walks).cuda(), torch.as_tensor(lens).cuda(), labels)
+    want = "".join(" ".join(str(int(labels[t])) for t in walks[i, :lens[i]]) + "\n" for i in range(n))
+    assert c.format_walks().cpu().numpy().tobytes().decode() == want
+    p = tmp_path / "w.txt"
+    c.save_walks(str(p), chunk_walks=300)
+    assert p.read_text() == want
+    c2 = WalkCorpus(c.walks, c.lens, None)                # no labels: compact ids
+    assert c2.format_walks(0, 3).cpu().numpy().tobytes().decode() == "".join(
+        " ".join(str(int(t)) for t in walks[i, :lens[i]]) + "\n" for i in range(3))
