@@ -222,6 +222,20 @@ int n2v_format_walks_write(const int32_t *walks, const int32_t *lens, int64_t n_
                            const int64_t *labels, const int64_t *tok_off, unsigned char *out,
                            void *stream);
 
+/* Parser of the same file (what LineSentence, src/main_link.py:340,346, does for a walk file):
+ * whitespace-separated integer tokens, one sentence per line.
+ *  1. n2v_parse_walks_index: flags + exclusive scans over the n_bytes+1 positions;
+ *     tok_idx[n_bytes] = number of tokens, line_idx[n_bytes] = number of lines;
+ *  2. n2v_parse_walks_fill: labels int64[n_tokens], sent_off int64[n_lines] = tokens before each
+ *     line (append n_tokens to close the last line); *bad_flag set on a non-integer token. */
+size_t n2v_parse_workspace_bytes(int64_t n_bytes);
+int n2v_parse_walks_index(const unsigned char *text, int64_t n_bytes, int32_t *tok_flag, int32_t *line_flag,
+                          int64_t *tok_idx, int64_t *line_idx, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int n2v_parse_walks_fill(const unsigned char *text, int64_t n_bytes, const int32_t *tok_flag,
+                         const int32_t *line_flag, const int64_t *tok_idx, const int64_t *line_idx,
+                         int64_t *labels, int64_t *sent_off, int *bad_flag, void *stream);
+
 /* ---- measurement helpers -------------------------------------------------------------------
  * Random-access HBM roofline denominators: mode 0 = one random 32-byte sector
  * read per access; mode 1 = random 512-byte row read-modify-write. buf holds n_bytes;

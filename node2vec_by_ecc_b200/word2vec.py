@@ -322,6 +322,11 @@ class Word2Vec:
             n_ids = int(len(labels)) if labels is not None else int(sentences.walks.max().item()) + 1
             words = [str(l) for l in (labels.tolist() if labels is not None else range(n_ids))]
             return sentences.walks, None, int(sentences.walks.shape[1]), int(sentences.walks.shape[0]), words
+        if isinstance(sentences, LineSentence) and isinstance(sentences.source, (str, os.PathLike)) \
+                and sentences.limit is None:
+            fast = self._ingest_walk_file(sentences, dev)
+            if fast is not None:
+                return fast
         # generic iterable of iterables of tokens (materialised once: py3 `map` objects are one-shot,
         # gensim needs >= 2 passes -- SURVEY.md section 2)
         ids = {}
@@ -339,6 +344,46 @@ class Word2Vec:
         tok = torch.as_tensor(np.asarray(toks, dtype=np.int32)).to(dev)
         off = torch.as_tensor(np.asarray(offs, dtype=np.int64)).to(dev)
         return tok, off, 0, len(offs) - 1, words
+
+    def _ingest_walk_file(self, ls, dev):
+        """LineSentence over a file of integer tokens (a walk file): tokenised on the device
+        (n2v_parse_walks_*). Returns None when a token is not an integer (generic path then)."""
+        L = lib()
+        raw = np.fromfile(ls.source, dtype=np.uint8)
+        n = int(raw.shape[0])
+        if n == 0 or n > (1 << 31):
+            return None
+        text = torch.as_tensor(raw).to(dev)
+        tf = torch.empty(n + 1, dtype=torch.int32, device=dev); lf = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        ti = torch.empty(n + 1, dtype=torch.int64, device=dev); li = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        ws_bytes = int(L.n2v_parse_workspace_bytes(C.c_int64(n)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.n2v_parse_walks_index(ptr(text), C.c_int64(n), ptr(tf), ptr(lf), ptr(ti), ptr(li), ptr(ws),
+                                      C.c_size_t(ws_bytes), stream()))
+        n_tok, n_lines = int(ti[-1].item()), int(li[-1].item())
+        labels = torch.empty(max(n_tok, 1), dtype=torch.int64, device=dev)
+        off = torch.empty(n_lines + 1, dtype=torch.int64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(L.n2v_parse_walks_fill(ptr(text), C.c_int64(n), ptr(tf), ptr(lf), ptr(ti), ptr(li), ptr(labels),
+                                     ptr(off), ptr(bad), stream()))
+        if int(bad.item()):
+            return None
+        off[n_lines] = n_tok
+        labels = labels[:n_tok]
+        lens = off[1:] - off[:-1]
+        if int(lens.max().item()) > ls.max_sentence_length:      # LineSentence splits long lines
+            return None
+        off = torch.cat([off[:1], off[1:][lens > 0]])           # empty lines yield no sentence
+        # ids in first-seen order, exactly like the generic path
+        uniq, inv = torch.unique(labels, return_inverse=True)
+        first = torch.full((uniq.numel(),), n_tok, dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, inv, torch.arange(n_tok, device=dev), reduce="amin")
+        order = torch.argsort(first)
+        id_of_uniq = torch.empty_like(order)
+        id_of_uniq[order] = torch.arange(order.numel(), device=dev)
+        tok = id_of_uniq[inv].to(torch.int32).contiguous()
+        words = [str(v) for v in uniq[order].tolist()]
+        return tok, off.contiguous(), 0, int(off.numel() - 1), words
 
     def build_vocab(self, sentences, **_):
         """scan_vocab + scale_vocab + finalize_vocab (word2vec.py): count, drop < min_count, sort by

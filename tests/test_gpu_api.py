@@ -208,3 +208,29 @@ def test_device_walk_formatter_matches_python_join(tmp_path):
     c2 = WalkCorpus(c.walks, c.lens, None)                # no labels: compact ids
     assert c2.format_walks(0, 3).cpu().numpy().tobytes().decode() == "".join(
         " ".join(str(int(t)) for t in walks[i, :lens[i]]) + "\n" for i in range(3))
+
+
+def test_walk_file_device_parser_equals_generic_path(tmp_path):
+    """LineSentence over an integer walk file is tokenised on the device (n2v_parse_walks_*): same
+    tokens, sentences, vocabulary order and trained rows as the generic Python path; tabs, blank
+    lines, CRLF, a missing final newline and negative labels included"""
+    from node2vec_by_ecc_b200 import LineSentence, Word2Vec
+    rng = np.random.RandomState(3)
+    lines = [" ".join(str(int(v)) for v in rng.randint(0, 50, size=rng.randint(1, 40))) for _ in range(200)]
+    lines[3] = ""                                   # blank line: no sentence
+    lines[5] = "7\t8   9 \r"                        # tabs, runs of spaces, CR
+    lines[9] = "-3 4 99999991234 -3"
+    text = "\n".join(lines)                         # no trailing newline
+    p = tmp_path / "walks.txt"
+    p.write_text(text)
+    m_fast = Word2Vec(LineSentence(str(p)), size=32, window=5, min_count=0, sg=1, iter=1, hogwild_warps=1)
+    sents = [l.split() for l in text.split("\n") if l.split()]
+    m_ref = Word2Vec(sents, size=32, window=5, min_count=0, sg=1, iter=1, hogwild_warps=1)
+    assert m_fast.corpus_count == m_ref.corpus_count == len(sents)
+    assert m_fast.wv.index2word == m_ref.wv.index2word
+    assert m_fast.pairs_trained == m_ref.pairs_trained and np.array_equal(m_fast.wv.syn0, m_ref.wv.syn0)
+    # a non-integer token falls back to the generic path
+    p2 = tmp_path / "words.txt"
+    p2.write_text("a b c\nb c d\n")
+    m2 = Word2Vec(LineSentence(str(p2)), size=8, window=2, min_count=0, sg=1, iter=1, hogwild_warps=1)
+    assert sorted(m2.wv.index2word) == ["a", "b", "c", "d"]
