@@ -234,3 +234,45 @@ def test_walk_file_device_parser_equals_generic_path(tmp_path):
     p2.write_text("a b c\nb c d\n")
     m2 = Word2Vec(LineSentence(str(p2)), size=8, window=2, min_count=0, sg=1, iter=1, hogwild_warps=1)
     assert sorted(m2.wv.index2word) == ["a", "b", "c", "d"]
+
+
+def test_user_edge_augmentation_matches_brute_force():
+    """add_user_edge's selections (main_link.py:358-453) on the device vs the reference's loops
+    restated with numpy/scipy"""
+    from scipy.stats import pearsonr
+    from node2vec_by_ecc_b200 import KeyedVectors, Vocab
+    from node2vec_by_ecc_b200.augment import as_tuples, user_edges
+    rng = np.random.RandomState(4)
+    U, d = 150, 32
+    kv = KeyedVectors(d)
+    kv.index2word = [str(i) for i in range(U + 20)]
+    kv.vocab = {w: Vocab(i, 1) for i, w in enumerate(kv.index2word)}
+    kv.syn0 = rng.randn(U + 20, d).astype(np.float32)
+    users = list(range(5, 5 + U))
+
+    def sim(a, b, method):
+        x, y = kv[str(a)].astype(np.float64), kv[str(b)].astype(np.float64)
+        return pearsonr(x, y)[0] if method == "pearson" else float(x @ y / np.linalg.norm(x) / np.linalg.norm(y))
+
+    for method in ("cos", "pearson"):
+        M = np.array([[0.0 if a == b else sim(a, b, method) for b in users] for a in users])
+        # ratio: top int(U * ratio) per user, weight 1
+        got = as_tuples(users, *user_edges(kv, users, "ratio", 0.04, method, block_rows=64))
+        k = int(U * 0.04)
+        assert len(got) == U * k
+        for i, u in enumerate(users):
+            mine = {b for a, b, _ in got[i * k:(i + 1) * k]}
+            want = {users[j] for j in np.argsort(-M[i], kind="stable")[:k]}
+            assert mine == want and all(a == u and w == 1.0 for a, _, w in got[i * k:(i + 1) * k])
+        # step / relu: similarity above a threshold
+        thre = 0.3
+        for mode in ("step", "relu"):
+            got = as_tuples(users, *user_edges(kv, users, mode, thre, method, block_rows=64))
+            want = {(users[i], users[j]) for i in range(U) for j in range(U) if M[i, j] > thre + 1e-6}
+            loose = {(users[i], users[j]) for i in range(U) for j in range(U) if M[i, j] > thre - 1e-6}
+            pairs = {(a, b) for a, b, _ in got}
+            assert want <= pairs <= loose
+            for a, b, w in got[:200]:
+                assert abs(w - (1.0 if mode == "step" else M[users.index(a), users.index(b)])) < 1e-5
+    got = user_edges(kv, users[:20], "linear", None, "cos")
+    assert got[0].numel() == 400
