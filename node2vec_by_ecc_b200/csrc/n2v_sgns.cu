@@ -25,26 +25,14 @@ constexpr int SGNS_BLOCK = 128;          // 4 warps
 constexpr int SGNS_MAX_NEG = 16;
 constexpr int SGNS_SMEM_TOKENS = 256;    // per-warp staging of the kept tokens of a sentence chunk
 
-__device__ float g_exp_table[EXP_TABLE_SIZE];
-static bool g_exp_table_ready[64] = {false};
-
-// word2vec_inner.pyx init(): EXP_TABLE[i] = exp((i / 1000 * 2 - 1) * 6); x / (x + 1) -- computed
-// on the host with the same float32 casts as the Cython code, then uploaded.
-static int ensure_exp_table(cudaStream_t stream)
+// word2vec_inner.pyx init(): EXP_TABLE[i] = exp((i / 1000 * 2 - 1) * 6); then x / (x + 1), with the
+// Cython code's float32 casts (float argument, C double exp, float result, float division).
+// Every block rebuilds its shared-memory copy: 8 exps per thread, no global state, no host sync.
+__device__ __forceinline__ float exp_table_entry(int i)
 {
-    int dev = 0;
-    N2V_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && g_exp_table_ready[dev]) return N2V_OK;
-    static float host_table[EXP_TABLE_SIZE];
-    for (int i = 0; i < EXP_TABLE_SIZE; ++i) {
-        float e = (float)exp(((float)i / (float)EXP_TABLE_SIZE * 2 - 1) * MAX_EXP);
-        host_table[i] = (float)(e / (e + 1));
-    }
-    N2V_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_exp_table, host_table, sizeof(host_table), 0,
-                                           cudaMemcpyHostToDevice, stream));
-    N2V_CHECK_CUDA(cudaStreamSynchronize(stream));   // host_table is static, one-time per device
-    if (dev < 64) g_exp_table_ready[dev] = true;
-    return N2V_OK;
+    const float x = __fmul_rn(__fadd_rn(__fmul_rn(__fdiv_rn((float)i, (float)EXP_TABLE_SIZE), 2.0f), -1.0f), (float)MAX_EXP);
+    const float e = (float)exp((double)x);
+    return __fdiv_rn(e, __fadd_rn(e, 1.0f));
 }
 
 // ---- vocabulary ---------------------------------------------------------------------------------
@@ -364,7 +352,7 @@ sgns_train_kernel(SgnsArgs a)
     __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ float s_exp[EXP_TABLE_SIZE];
-    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = exp_table_entry(i);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -449,7 +437,7 @@ sgns_train_kernel_v2(SgnsArgs a)
     __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ float s_exp[EXP_TABLE_SIZE];
-    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = exp_table_entry(i);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -598,7 +586,7 @@ sgns_train_kernel_v3(SgnsArgs a)
     // the carried rows as first read (one reduction of out - orig per row at the end of a centre):
     // parked in shared memory, each lane touches only its own 16 bytes -- keeps 24 registers free
     __shared__ float4 s_orig[SGNS_BLOCK / 32][FN + 1][32];
-    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = g_exp_table[i];
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = exp_table_entry(i);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -882,8 +870,6 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
     N2V_REQUIRE(p.grid_warps >= 1 && p.total_examples >= 1 && p.sent_per_job >= 1, "bad schedule");
     N2V_REQUIRE(p.bucket_bits >= 1 && p.bucket_bits <= 24, "bucket_bits out of range");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    int rc = ensure_exp_table(stream);
-    if (rc) return rc;
     SgnsArgs a{tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table,
                bucket_lo, p, syn0, syn1neg, pairs_out};
     const int nv = (p.dim + 127) / 128;
