@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--hogwild-warps", type=int, default=0)
     ap.add_argument("--atomic", type=int, default=1)
     ap.add_argument("--shared-negatives", type=int, default=1)
+    ap.add_argument("--sync-every", type=int, default=1, help="average the replicated tables every K steps (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -219,7 +220,7 @@ def run_ours(a):
                       grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
                       atomic_updates=a.atomic, negative_sharing=mode["shared"])
         e3.record()
-        if world > 1:                                        # replicated tables, averaged
+        if world > 1 and (i + 1) % max(1, a.sync_every) == 0:   # replicated tables, averaged
             # on a side stream: the all-reduce overlaps the NEXT step's walk kernel, which does not
             # touch the tables; the next SGNS launch waits for it
             ready = torch.cuda.Event(); ready.record()
@@ -337,7 +338,7 @@ def run_ours(a):
             "walk_steps_per_s": (float(cn[0]) if tables is None else S * world) / (walk_ms / 1e3),
             "sgns_pairs_per_s_kernel": pairs / (sgns_ms / 1e3),
             "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other, "gpu_launches": 2 * a.steps,
-            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
+            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "sync_every": a.sync_every, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
         }
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a, dg, trainer, walks)
