@@ -13,7 +13,7 @@ path over one batch: `batch_walks` walks per GPU are simulated (n2v_walk_reject)
 trained on (n2v_sgns_train); with N > 1 the walk ids of a step are split across ranks (weak
 scaling: batch per GPU fixed) and the replicated tables are averaged by an NCCL all-reduce every
 step. value = (centre, context) pairs trained per second through the whole step, all ranks.
-Inputs are larger than L2 (tables 2 x 2.1 GB, CSR 0.8 GB), no L2 flush needed.
+Inputs are larger than L2 (tables 2 x 1.35 GB, CSR 0.8 GB, arc hash 4.3 GB), no L2 flush needed.
 """
 from __future__ import annotations
 
@@ -126,6 +126,8 @@ def config_of(a, n_nodes=None, nnz=None):
                      f"p={a.p} q={a.q}, R={a.num_walks} L={a.walk_length}; SGNS d={a.dim} window={a.window} "
                      f"negative={a.negative} sample=1e-3",
          "batch_walks_per_gpu": a.batch_walks, "generator": "node2vec_by_ecc_b200.synth.rmat_edges seed=1",
+         "sgns_negatives": ("one set of 5 per centre, shared by its context pairs (other_negative_mode = fresh set per pair)"
+                            if a.shared_negatives else "fresh set of 5 per (centre, context) pair, gensim's law"),
          "l2": "inputs larger than L2 (no flush)"}
     if n_nodes is not None:
         c["n_nodes"], c["nnz"] = n_nodes, nnz
