@@ -41,10 +41,17 @@ __device__ __forceinline__ void finish_table(int64_t K, double *wq, int32_t *wJ,
                                              bool normalize = true)
 {
     __syncwarp();
-    // B: norm_const = sum(unnormalized_probs), left to right (node2vec.py:148,:186)
+    // B: norm_const = sum(unnormalized_probs), left to right (node2vec.py:148,:186). 32 values per
+    // coalesced load; every lane then adds them in index order (identical norm on all lanes).
     double norm = 0.0;
-    if (normalize)
-        for (int64_t k = 0; k < K; ++k) norm = __dadd_rn(norm, wq[k]);
+    if (normalize) {
+        for (int64_t k0 = 0; k0 < K; k0 += 32) {
+            const double v = (k0 + lane < K) ? wq[k0 + lane] : 0.0;
+            const int m = (K - k0 < 32) ? (int)(K - k0) : 32;
+#pragma unroll 8
+            for (int j = 0; j < m; ++j) norm = __dadd_rn(norm, __shfl_sync(0xFFFFFFFFu, v, j));
+        }
+    }
     // C: normalized = float(u)/norm (:149); q[kk] = K*prob (:253); classify (:254-257)
     const double Kd = (double)K;
     for (int64_t k = lane; k < K; k += 32) {
@@ -52,34 +59,45 @@ __device__ __forceinline__ void finish_table(int64_t K, double *wq, int32_t *wJ,
         wq[k] = qq;
         wJ[k] = (qq < 1.0) ? MARK_SMALL : MARK_LARGE;
     }
-    __syncwarp();
-    // D: while len(smaller) > 0 and len(larger) > 0 (:259-268)
-    if (lane == 0) {
-        int64_t si = K - 1, li = K - 1, pending = -1, cur_large = -1;
-        double q_large = 0.0;                      // q of the current large lives in a register
+    // D: while len(smaller) > 0 and len(larger) > 0 (:259-268). Warp-uniform: every lane runs the
+    // same control flow on the same registers; the two downward scans read the class marks 32 at a
+    // time (one coalesced load + ballot per block) and pop them with clz; q of the running large
+    // and of a demoted large stay in registers; lane 0 does the stores.
+    {
+        auto block_mask = [&](int64_t blk, int mark) -> uint32_t {
+            __syncwarp();                                   // lane 0's stores visible to the block load
+            const int64_t k = (blk << 5) + lane;
+            return __ballot_sync(0xFFFFFFFFu, k < K && wJ[k] == mark);
+        };
+        int64_t sb = (K - 1) >> 5, lb = sb;
+        uint32_t smask = block_mask(sb, MARK_SMALL), lmask = block_mask(lb, MARK_LARGE);
+        int64_t pending = -1, cur_large = -1;
+        double q_large = 0.0, q_pending = 0.0;
         for (;;) {
-            int64_t small;
-            if (pending >= 0) small = pending;
+            int64_t small; double q_small;
+            if (pending >= 0) { small = pending; q_small = q_pending; }
             else {
-                while (si >= 0 && wJ[si] != MARK_SMALL) --si;
-                if (si < 0) break;
-                small = si;
+                while (smask == 0 && sb > 0) { --sb; smask = block_mask(sb, MARK_SMALL); }
+                if (smask == 0) break;
+                small = (sb << 5) + (31 - __clz(smask));    // top of `smaller`: highest index first
+                q_small = wq[small];
             }
             if (cur_large < 0) {
-                while (li >= 0 && wJ[li] != MARK_LARGE) --li;
-                if (li < 0) break;
-                cur_large = li--;
+                while (lmask == 0 && lb > 0) { --lb; lmask = block_mask(lb, MARK_LARGE); }
+                if (lmask == 0) break;
+                const int bit = 31 - __clz(lmask);
+                cur_large = (lb << 5) + bit; lmask &= ~(1u << bit);
                 q_large = wq[cur_large];
             }
-            if (pending >= 0) pending = -1; else --si;
-            wJ[small] = (int32_t)cur_large;                                   // J[small] = large
-            q_large = __dadd_rn(__dadd_rn(q_large, wq[small]), -1.0);         // q[large]+q[small]-1.0
+            if (pending >= 0) pending = -1; else smask &= ~(1u << (int)(small & 31));
+            if (lane == 0) wJ[small] = (int32_t)cur_large;                   // J[small] = large
+            q_large = __dadd_rn(__dadd_rn(q_large, q_small), -1.0);          // q[large]+q[small]-1.0
             if (q_large < 1.0) {
-                wq[cur_large] = q_large; wJ[cur_large] = MARK_DEMOTED;
-                pending = cur_large; cur_large = -1;
+                if (lane == 0) { wq[cur_large] = q_large; wJ[cur_large] = MARK_DEMOTED; }
+                pending = cur_large; q_pending = q_large; cur_large = -1;
             }
         }
-        if (cur_large >= 0) wq[cur_large] = q_large;
+        if (cur_large >= 0 && lane == 0) wq[cur_large] = q_large;
     }
     __syncwarp();
     // E: leftovers keep J = 0 (np.zeros, :248); pack

@@ -50,6 +50,8 @@ torch.cuda.empty_cache()
 def alias_case(name, lo, hi, n, p, q, R, L):
     dg = DeviceGraph.from_coo(lo, hi, None, n, undirected=True)
     tot = dg.sum_deg_sq()
+    if tot < 2e8:
+        dg.build_alias_tables(p, q)                 # warm-up: module load, allocator
     torch.cuda.synchronize(); t0 = time.time()
     t = dg.build_alias_tables(p, q)
     torch.cuda.synchronize(); build_s = time.time() - t0
