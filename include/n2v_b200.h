@@ -71,9 +71,9 @@ int n2v_etab_offsets(const int64_t *row_ptr, const int32_t *col, int32_t n_nodes
 /* replaces: per-node loop of preprocess_transition_probs (node2vec.py:184-188) and of
  * preprocess_transition_probs_popularity (:213-218, popwalk bit 0; is_item[v] != 0 marks the
  * '9999999'-prefixed item nodes). popwalk bit 1: the weights already are probabilities, skip
- * the normalisation -- then each row is exactly alias_setup(probs) (node2vec.py:240-269). slots[nnz] laid out like col. Optional raw outputs
- * J_raw int32[nnz] / q_raw float64[nnz] (the reference's (J, q)); when NULL, work_J / work_q
- * scratch of the same sizes must be given instead. */
+ * the normalisation -- then each row is exactly alias_setup(probs) (node2vec.py:240-269).
+ * slots[nnz] is laid out like col. work_J int32[nnz] / work_q float64[nnz] are scratch that
+ * holds, on return, the reference's raw (J, q) of every node table. */
 int n2v_alias_build_nodes(const int64_t *row_ptr, const int32_t *col, const double *w,
                           int32_t n_nodes, const uint8_t *is_item, int popwalk,
                           n2v_slot_t *slots, int32_t *work_J, double *work_q, void *stream);
