@@ -11,8 +11,10 @@ edges after symmetrise/dedup, rejection-sampling walker, p=0.25 q=4, R=10 walks 
 SGNS d=128 window=10 negative=5 sample=1e-3 (the main.py defaults). A STEP is one pass of the hot
 path over one batch: `batch_walks` walks per GPU are simulated (n2v_walk_reject) and the batch is
 trained on (n2v_sgns_train); with N > 1 the walk ids of a step are split across ranks (weak
-scaling: batch per GPU fixed) and the replicated tables are averaged by an NCCL all-reduce every
-step. value = (centre, context) pairs trained per second through the whole step, all ranks.
+scaling: batch per GPU fixed) and the replicated tables are combined by a delta-sum NCCL
+all-reduce every `sync_walks` walks per rank (default: the largest interval that keeps
+link-prediction AUC within +-0.005 of one replica, node2vec_by_ecc_b200.dist).
+value = (centre, context) pairs trained per second through the whole step, all ranks.
 Inputs are larger than L2 (tables 2 x 1.35 GB, CSR 0.8 GB, arc hash 4.3 GB), no L2 flush needed.
 """
 from __future__ import annotations
@@ -62,7 +64,9 @@ def parse():
     ap.add_argument("--hogwild-warps", type=int, default=0)
     ap.add_argument("--atomic", type=int, default=1)
     ap.add_argument("--shared-negatives", type=int, default=1)
-    ap.add_argument("--sync-every", type=int, default=1, help="average the replicated tables every K steps (N > 1)")
+    ap.add_argument("--sync-walks", type=int, default=0,
+                    help="walks per rank between two delta-sum syncs of the replicated tables (N > 1); "
+                         "0 = auto (total pairs per sync <= 100 V / N), -1 = once per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -198,8 +202,15 @@ def run_ours(a):
     kern = {"walk": [], "sgns": []}
 
     mode = {"shared": int(a.shared_negatives)}
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    pending = {"ev": None}
+    from node2vec_by_ecc_b200.dist import ReplicaSync, sync_walks_per_rank
+    replica_sync = ReplicaSync(trainer.syn0, trainer.syn1neg)
+    pairs_per_walk = (2 * a.window + 1) * L / 2.0            # ~ mean reduced window = (window + 1) / 2 each side
+    if world == 1 or a.sync_walks < 0:
+        sync_walks = B
+    elif a.sync_walks > 0:
+        sync_walks = min(B, a.sync_walks)
+    else:
+        sync_walks = min(B, sync_walks_per_rank(trainer.V, world, pairs_per_walk))
 
     def step(i, host_io=None, record=False):
         g0 = (i * world + rank) * B                         # global id of this rank's first walk
@@ -209,33 +220,29 @@ def run_ours(a):
             starts = dst.copy_(hs, non_blocking=True)
         else:
             starts = ((g0 + ar) % n).to(torch.int32)
-        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0, e1 = ev(), ev()
         e0.record(); do_walk(starts, g0); e1.record()
         if host_io is not None:                              # simulate_walks returns to the host,
             hw.copy_(walks, non_blocking=True); hl.copy_(lens, non_blocking=True)   # learn_embeddings
             walks.copy_(hw, non_blocking=True)               # takes them back in
-        e2.record()
-        if pending["ev"] is not None:                        # tables of the previous step averaged?
-            torch.cuda.current_stream().wait_event(pending["ev"]); pending["ev"] = None
-        trainer.train(walks, None, B, L, total_examples=total_walks, example_base=g0 % total_walks,
-                      sent_id_base=g0, sent_per_job=10000 // L,
-                      grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
-                      atomic_updates=a.atomic, negative_sharing=mode["shared"])
-        e3.record()
-        if world > 1 and (i + 1) % max(1, a.sync_every) == 0:   # replicated tables, averaged
-            # on a side stream: the all-reduce overlaps the NEXT step's walk kernel, which does not
-            # touch the tables; the next SGNS launch waits for it
-            ready = torch.cuda.Event(); ready.record()
-            with torch.cuda.stream(comm):
-                comm.wait_event(ready)
-                dist.all_reduce(trainer.syn0); dist.all_reduce(trainer.syn1neg)
-                trainer.syn0.mul_(1.0 / world); trainer.syn1neg.mul_(1.0 / world)
-                pending["ev"] = torch.cuda.Event(); pending["ev"].record(comm)
+        # SGNS in sub-batches of `sync_walks`, tables combined (delta-sum) after each (N > 1)
+        for sa in range(0, B, sync_walks):
+            sb_ = min(B, sa + sync_walks)
+            e2, e3 = ev(), ev()
+            e2.record()
+            trainer.train(walks[sa:sb_], None, sb_ - sa, L, total_examples=total_walks,
+                          example_base=(g0 + sa) % total_walks, sent_id_base=g0 + sa, sent_per_job=10000 // L,
+                          grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
+                          atomic_updates=a.atomic, negative_sharing=mode["shared"])
+            e3.record()
+            replica_sync.sync()
+            if record:
+                kern["sgns"].append((e2, e3))
         if host_io is not None:
             hp.copy_(trainer.pairs[:1], non_blocking=True)
             torch.cuda.current_stream().synchronize()        # the caller reads the result
         if record:
-            kern["walk"].append((e0, e1)); kern["sgns"].append((e2, e3))
+            kern["walk"].append((e0, e1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -312,11 +319,11 @@ def run_ours(a):
             kname = "sgns_train_kernel_v2 (per-pair negatives)"
         sg_gbs = alg_bytes / (sgns_ms / 1e3) / 1e9
         roof = {"kernel": kname, "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
-                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]) if (a.scale == 22 and a.batch_walks == 1 << 19) else None,
+                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]) if (a.scale == 22 and a.batch_walks == 1 << 19 and world == 1) else None,
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)", "peak_source": src,
-                "algorithmic_bytes_per_launch": alg_bytes / a.steps,
-                "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / a.steps,
-                "centres_per_launch": centres / world / a.steps, "ms_per_launch": sgns_ms / a.steps,
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, len(kern["sgns"])),
+                "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / max(1, len(kern["sgns"])),
+                "centres_per_launch": centres / world / max(1, len(kern["sgns"])), "ms_per_launch": sgns_ms / max(1, len(kern["sgns"])),
                 "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (sgns_ms / 1e3) / 1e9}
         if tables is None:
             S, T, P = (float(cn[0]) / world, float(cn[1]) / world, float(cn[3]) / world)
@@ -327,7 +334,7 @@ def run_ours(a):
             wbytes = BYTES_PER_ALIAS_STEP * S
         w_gbs = wbytes / (walk_ms / 1e3) / 1e9
         roof_walk = {"kernel": ("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode), "bound": "hbm", "achieved": w_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode) if (a.scale == 22 and a.batch_walks == 1 << 19) else None,
+                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode) if (a.scale == 22 and a.batch_walks == 1 << 19 and world == 1) else None,
                      "algorithmic_bytes_per_launch": wbytes / a.steps,
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}
@@ -339,8 +346,11 @@ def run_ours(a):
             "config": config_of(a, n, dg.nnz),
             "walk_steps_per_s": (float(cn[0]) if tables is None else S * world) / (walk_ms / 1e3),
             "sgns_pairs_per_s_kernel": pairs / (sgns_ms / 1e3),
-            "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other, "gpu_launches": 2 * a.steps,
-            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "sync_every": a.sync_every, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
+            "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other,
+            "gpu_launches": a.steps * (1 + (B + sync_walks - 1) // sync_walks),
+            "multi_gpu_sync": None if world == 1 else {"rule": "delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,
+                                                        "syncs_per_step": (B + sync_walks - 1) // sync_walks},
+            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
         }
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a, dg, trainer, walks)

@@ -5,7 +5,13 @@ same host logic runs under gloo in the CPU tests).
   applies across its process pool -- with no communication; Philox counters are keyed by the
   global id, so the corpus does not depend on the number of ranks;
 * SGNS shards the walk corpus; vocabulary counts are summed once (all_reduce of int64[N]); the
-  replicated syn0 / syn1neg tables are averaged every K steps (all_reduce(sum) * 1/world).
+  replicated syn0 / syn1neg tables are combined by DELTA-SUM every few thousand walks:
+  new = base + sum over ranks of (replica - base). Plain parameter averaging (all_reduce * 1/world,
+  the scheme SURVEY.md 8e sketches) divides every row's update by `world` because a row is usually
+  touched by one replica per interval; measured on a 1 M-node planted graph it loses 0.04 AUC at 2
+  replicas and collapses at 8, whatever the interval, while delta-sum stays within +-0.005 of the
+  single-replica run when the interval obeys total pairs per sync <= ~100 * V / world
+  (scripts/auc_multi_replica_large.py, profiles/r01_o_multi_replica_auc.txt).
 """
 from __future__ import annotations
 
@@ -41,8 +47,35 @@ def sum_counts(counts: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+def sync_walks_per_rank(vocab_size: int, world_size: int, pairs_per_walk: float, factor: float = 100.0) -> int:
+    """Walks one rank may train on between two delta-sum syncs while the replicas stay within the
+    +-0.005 AUC band: total pairs per sync <= factor * V / world."""
+    if world_size <= 1:
+        return 1 << 62
+    return max(256, int(factor * vocab_size / (world_size * world_size) / max(pairs_per_walk, 1.0)))
+
+
+class ReplicaSync:
+    """Delta-sum synchronisation of replicated tables: after sync() every rank holds
+    base + sum_r (replica_r - base), computed as all_reduce(sum of replicas) - (world-1) * base."""
+
+    def __init__(self, *tables: torch.Tensor):
+        self.tables = tables
+        self.world = world()[1]
+        self.bases = [t.clone() for t in tables] if self.world > 1 else []
+
+    def sync(self):
+        if self.world == 1:
+            return
+        for t, b in zip(self.tables, self.bases):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.add_(b, alpha=-(self.world - 1))
+            b.copy_(t)
+
+
 def average_tables(*tables: torch.Tensor):
-    """Parameter averaging of replicated tables, in place."""
+    """Plain parameter averaging, in place (kept for comparison; see the module docstring for why
+    ReplicaSync is what the trainers use)."""
     _, w = world()
     if w == 1:
         return

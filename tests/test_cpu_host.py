@@ -88,6 +88,16 @@ def test_walk_corpus_sequence_view():
     assert len(c) == 3 and c[2] == [10, 20] and c.num_steps() == 3
 
 
+def test_sync_interval_rule():
+    from node2vec_by_ecc_b200.dist import sync_walks_per_rank
+    assert sync_walks_per_rank(10 ** 6, 1, 400.0) > 10 ** 12          # one replica: never
+    # total pairs per sync <= 100 V / world  (the emulated +-0.005 AUC band)
+    for w in (2, 4, 8):
+        walks = sync_walks_per_rank(10 ** 6, w, 396.0)
+        assert walks * w * 396.0 <= 100 * 10 ** 6 / w * 1.01
+    assert sync_walks_per_rank(1000, 8, 836.0) == 256                 # floor
+
+
 def test_shard_range_matches_main_link_partition():
     from node2vec_by_ecc_b200.dist import shard_range, step_walk_ids
     import math
@@ -111,7 +121,7 @@ def _free_port():
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from node2vec_by_ecc_b200.dist import average_tables, shard_range, sum_counts
+    from node2vec_by_ecc_b200.dist import ReplicaSync, average_tables, shard_range, sum_counts
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     a, b = shard_range(10, rank, world)
     counts = torch.zeros(10, dtype=torch.int64)
@@ -120,7 +130,19 @@ def _gloo_worker(rank, world, port, q):
     t0 = torch.full((4, 8), float(rank + 1))
     t1 = torch.full((4, 8), float(10 * (rank + 1)))
     average_tables(t0, t1)
-    q.put((rank, counts.tolist(), float(t0[0, 0]), float(t1[0, 0])))
+    # delta-sum: every rank starts from the same base and adds its own delta
+    base = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    rep = base.clone()
+    sync = ReplicaSync(rep)
+    rep += float(rank + 1)                       # this replica's training moved every entry by rank+1
+    sync.sync()
+    ok1 = bool(torch.equal(rep, base + 3.0))     # base + (1 + 2)
+    rep[rank] += 10.0                            # second interval: disjoint rows
+    sync.sync()
+    want = base + 3.0
+    want[0] += 10.0; want[1] += 10.0
+    ok2 = bool(torch.equal(rep, want)) and bool(torch.equal(sync.bases[0], want))
+    q.put((rank, counts.tolist(), float(t0[0, 0]), float(t1[0, 0]), ok1 and ok2))
     dist.destroy_process_group()
 
 
@@ -136,9 +158,10 @@ def test_gloo_world2_counts_and_table_averaging():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, counts, a0, a1 in res:
+    for rank, counts, a0, a1, delta_ok in res:
         assert counts == list(range(1, 11))          # disjoint shards summed
         assert a0 == 1.5 and a1 == 15.0              # (1+2)/2, (10+20)/2
+        assert delta_ok                              # ReplicaSync: base + sum of deltas on every rank
 
 
 def test_bench_reference_arm_contract_small():
