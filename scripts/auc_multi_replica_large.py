@@ -68,7 +68,12 @@ def run(W, combine, interval):
             for g0 in range(ra_, rb_, B):
                 nb = min(B, rb_ - g0); walk(g0, nb)
                 tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=250, negative_sharing=1)
-            acc0 += tr.syn0 - base0; acc1 += tr.syn1neg - base1
+            d0, d1 = tr.syn0 - base0, tr.syn1neg - base1
+            if os.environ.get("BF16_DELTAS"):          # what a bf16 all-reduce of the deltas would carry
+                d0, d1 = d0.bfloat16().float(), d1.bfloat16().float()
+            acc0 += d0; acc1 += d1
+            if os.environ.get("BF16_DELTAS"):
+                acc0, acc1 = acc0.bfloat16().float(), acc1.bfloat16().float()
         sc = 1.0 / W if combine == "avg" else 1.0
         tr.syn0.copy_(base0 + sc * acc0); tr.syn1neg.copy_(base1 + sc * acc1)
         del base0, base1, acc0, acc1
