@@ -36,6 +36,7 @@ def walk(g0, nb):
     st = ((g0 + torch.arange(nb, device=dev)) % n).to(torch.int32)
     dg.walk_reject(0.25, 4.0, st, L, 1, g0, out=(walks[:nb], lens[:nb]))
 
+GW = int(os.environ.get("GRID_WARPS", "0")) or None
 counts = torch.zeros(n, dtype=torch.int64, device=dev)
 for g0 in range(0, total, B):
     nb = min(B, total - g0); walk(g0, nb)
@@ -51,6 +52,7 @@ def auc_of(tr):
     return float(roc_auc_score(y, s))
 
 def run(W, combine, interval):
+    global GW
     tr = SgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=1)
     step_walks = interval * W
     for s0 in range(0, total, step_walks):
@@ -58,7 +60,7 @@ def run(W, combine, interval):
         if W == 1:
             for g0 in range(s0, s1, B):
                 nb = min(B, s1 - g0); walk(g0, nb)
-                tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=250, negative_sharing=1)
+                tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=250, negative_sharing=int(os.environ.get("SHARED", "1")), grid_warps=GW)
             continue
         base0, base1 = tr.syn0.clone(), tr.syn1neg.clone()
         acc0, acc1 = torch.zeros_like(base0), torch.zeros_like(base1)
@@ -67,7 +69,7 @@ def run(W, combine, interval):
             ra_, rb_ = s0 + r * interval, min(s1, s0 + (r + 1) * interval)
             for g0 in range(ra_, rb_, B):
                 nb = min(B, rb_ - g0); walk(g0, nb)
-                tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=250, negative_sharing=1)
+                tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=250, negative_sharing=int(os.environ.get("SHARED", "1")), grid_warps=GW)
             d0, d1 = tr.syn0 - base0, tr.syn1neg - base1
             if os.environ.get("BF16_DELTAS"):          # what a bf16 all-reduce of the deltas would carry
                 d0, d1 = d0.bfloat16().float(), d1.bfloat16().float()
@@ -79,7 +81,9 @@ def run(W, combine, interval):
         del base0, base1, acc0, acc1
     return auc_of(tr)
 
-print(json.dumps({"n": n, "edges": int(lo.numel()), "walks": total, "W": 1, "auc": run(1, "avg", B)}), flush=True)
+print(json.dumps({"n": n, "edges": int(lo.numel()), "walks": total, "W": 1, "grid_warps": GW or "default", "auc": run(1, "avg", B)}), flush=True)
+if os.environ.get("ONLY_W1"):
+    sys.exit(0)
 grid = os.environ.get("GRID")
 cases = ([tuple(int(x) for x in c.split(":")) for c in grid.split(",")] if grid
          else [(W, iv) for W in (2, 8) for iv in (1 << 19, 1 << 16, 1 << 13)])
