@@ -64,6 +64,7 @@ def run(W, combine, interval):
             continue
         base0, base1 = tr.syn0.clone(), tr.syn1neg.clone()
         acc0, acc1 = torch.zeros_like(base0), torch.zeros_like(base1)
+        sq0 = torch.zeros(base0.shape[0], 1, device=dev); sq1 = torch.zeros_like(sq0)
         for r in range(W):
             tr.syn0.copy_(base0); tr.syn1neg.copy_(base1)
             ra_, rb_ = s0 + r * interval, min(s1, s0 + (r + 1) * interval)
@@ -74,10 +75,16 @@ def run(W, combine, interval):
             if os.environ.get("BF16_DELTAS"):          # what a bf16 all-reduce of the deltas would carry
                 d0, d1 = d0.bfloat16().float(), d1.bfloat16().float()
             acc0 += d0; acc1 += d1
+            sq0 += (d0 * d0).sum(1, keepdim=True); sq1 += (d1 * d1).sum(1, keepdim=True)
             if os.environ.get("BF16_DELTAS"):
                 acc0, acc1 = acc0.bfloat16().float(), acc1.bfloat16().float()
-        sc = 1.0 / W if combine == "avg" else 1.0
-        tr.syn0.copy_(base0 + sc * acc0); tr.syn1neg.copy_(base1 + sc * acc1)
+        if combine == "adapt":     # per-row redundancy c = |sum d|^2 / sum |d|^2 in [0, W]: identical deltas -> average, independent -> sum
+            c0 = ((acc0 * acc0).sum(1, keepdim=True) / sq0.clamp_min(1e-30)).clamp_(min=1.0)
+            c1 = ((acc1 * acc1).sum(1, keepdim=True) / sq1.clamp_min(1e-30)).clamp_(min=1.0)
+            tr.syn0.copy_(base0 + acc0 / c0); tr.syn1neg.copy_(base1 + acc1 / c1)
+        else:
+            sc = 1.0 / W if combine == "avg" else 1.0
+            tr.syn0.copy_(base0 + sc * acc0); tr.syn1neg.copy_(base1 + sc * acc1)
         del base0, base1, acc0, acc1
     return auc_of(tr)
 
@@ -88,7 +95,7 @@ grid = os.environ.get("GRID")
 cases = ([tuple(int(x) for x in c.split(":")) for c in grid.split(",")] if grid
          else [(W, iv) for W in (2, 8) for iv in (1 << 19, 1 << 16, 1 << 13)])
 for W, interval in cases:
-    for combine in (("sum",) if grid else ("avg", "sum")):
+    for combine in (tuple(os.environ.get("COMBINE", "sum").split(",")) if grid else ("avg", "sum")):
         for _ in (0,):
             t0 = time.time()
             print(json.dumps({"W": W, "combine": combine, "walks_per_replica_per_sync": interval, "auc": run(W, combine, interval),
