@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--sync-walks", type=int, default=0,
                     help="walks per rank between two delta-sum syncs of the replicated tables (N > 1); "
                          "0 = auto (total pairs per sync <= 100 V / N), -1 = once per step")
+    ap.add_argument("--multi-gpu-sgns", default="replica", choices=["peer", "replica"],
+                    help="N > 1: peer = one table pair sharded over the GPUs' HBM, trained over NVLink peer "
+                         "memory; replica = a full copy per GPU, delta-sum all-reduce every --sync-walks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -192,7 +195,12 @@ def run_ours(a):
         check(lib().n2v_vocab_count(ptr(walks), C.c_int64((e - s) * L), C.c_int32(n), ptr(counts), stream()))
     if world > 1:
         dist.all_reduce(counts)
-    trainer = SgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
+    peer = world > 1 and a.multi_gpu_sgns == "peer" and bool(a.shared_negatives)
+    if peer:      # ONE table pair spread over the GPUs' HBM, trained by all of them over NVLink
+        from node2vec_by_ecc_b200 import PeerSgnsTrainer
+        trainer = PeerSgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
+    else:
+        trainer = SgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
     grid_warps = a.hogwild_warps or trainer.default_hogwild_warps(bool(a.shared_negatives))
     counters.zero_()
     torch.cuda.synchronize()
@@ -203,9 +211,9 @@ def run_ours(a):
 
     mode = {"shared": int(a.shared_negatives)}
     from node2vec_by_ecc_b200.dist import ReplicaSync, sync_walks_per_rank
-    replica_sync = ReplicaSync(trainer.syn0, trainer.syn1neg)
+    replica_sync = None if peer else ReplicaSync(trainer.syn0, trainer.syn1neg)
     pairs_per_walk = (2 * a.window + 1) * L / 2.0            # ~ mean reduced window = (window + 1) / 2 each side
-    if world == 1 or a.sync_walks < 0:
+    if world == 1 or peer or a.sync_walks < 0:
         sync_walks = B
     elif a.sync_walks > 0:
         sync_walks = min(B, a.sync_walks)
@@ -235,7 +243,8 @@ def run_ours(a):
                           grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
                           atomic_updates=a.atomic, negative_sharing=mode["shared"])
             e3.record()
-            replica_sync.sync()
+            if replica_sync is not None:
+                replica_sync.sync()
             if record:
                 kern["sgns"].append((e2, e3))
         if host_io is not None:
@@ -293,7 +302,7 @@ def run_ours(a):
                "api": "DeviceGraph.walk_reject -> host -> SgnsTrainer.train (pinned host buffers)"}
 
     other = None
-    if not a.no_e2e:      # the other negative-sampling mode, same steps, kernel-timed
+    if not a.no_e2e and not peer:      # the other negative-sampling mode, same steps, kernel-timed
         kern_main = kern
         kern = {"walk": [], "sgns": []}
         mode["shared"] = 1 - mode["shared"]
@@ -348,8 +357,11 @@ def run_ours(a):
             "sgns_pairs_per_s_kernel": pairs / (sgns_ms / 1e3),
             "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other,
             "gpu_launches": a.steps * (1 + (B + sync_walks - 1) // sync_walks),
-            "multi_gpu_sync": None if world == 1 else {"rule": "delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,
-                                                        "syncs_per_step": (B + sync_walks - 1) // sync_walks},
+            "multi_gpu_sgns": None if world == 1 else (
+                {"tables": "one syn0/syn1neg pair, row i in GPU i % N's HBM, every GPU trains its own walks against all parts "
+                           "over NVLink peer memory (red.global.add.v4.f32); no replicas, no sync"} if peer else
+                {"tables": "replicated; delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,
+                 "syncs_per_step": (B + sync_walks - 1) // sync_walks}),
             "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
         }
         if not a.no_cpu_baseline and world == 1:

@@ -201,6 +201,22 @@ int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sen
                    const n2v_sgns_params_t *params, float *syn0, float *syn1neg,
                    unsigned long long *pairs_out, void *stream);
 
+/* Sharded tables: ONE logical syn0 / syn1neg pair spread over n_parts (1, 2, 4 or 8) allocations,
+ * vocabulary row i in part i % n_parts at local row i / n_parts. The parts may live on other GPUs
+ * of the node (peer memory mapped over NVLink, e.g. cudaIpcOpenMemHandle): every GPU then trains
+ * its own walks against the same tables with red.global.add over NVLink -- gensim's shared-memory
+ * Hogwild across GPUs, no replicas to reconcile. syn0_parts / syn1neg_parts are HOST arrays of
+ * n_parts device pointers. Shared-negative kernel only (negative_sharing = 1, dim <= 128, k = 5).
+ * n2v_sgns_init_part initialises one part (what n2v_sgns_init does for part 0 of 1). */
+int n2v_sgns_init_part(float *syn0_part, float *syn1neg_part, int32_t V, int32_t dim, uint64_t seed,
+                       int32_t part, int32_t n_parts, void *stream);
+int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                           int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                           const uint32_t *keep_thr, const uint32_t *cum_table, const int32_t *bucket_lo,
+                           const n2v_sgns_params_t *params, float *const *syn0_parts,
+                           float *const *syn1neg_parts, int32_t n_parts,
+                           unsigned long long *pairs_out, void *stream);
+
 /* ---- link scoring ---------------------------------------------------------------------------
  * replaces: link_score(emb, a, b) with link_method "cos" (src/main_link.py:43-49) over a batch of
  * pairs, as looped by get_roc_score (:173-189). a/b: row indices (-1 = word not in vocabulary ->

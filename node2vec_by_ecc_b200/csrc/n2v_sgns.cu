@@ -14,6 +14,7 @@
 // instruction), dots are reduced with 5 xor-shuffles. The kernel is HBM random-row bound
 // (0.64 flop/B); tensor cores do not apply.
 #include <cub/cub.cuh>
+#include <type_traits>
 
 #include "n2v_common.cuh"
 
@@ -91,14 +92,15 @@ __global__ void sgns_bucket_kernel(const uint32_t *__restrict__ cum_table, int32
     bucket_lo[b] = lo;
 }
 
-__global__ void sgns_init_kernel(float *__restrict__ syn0, float *__restrict__ syn1neg, int32_t V,
-                                 int32_t dim, uint32_t k0, uint32_t k1)
+// rows of this table: local row l holds vocabulary row l * n_parts + part (n_parts = 1: the whole table)
+__global__ void sgns_init_kernel(float *__restrict__ syn0, float *__restrict__ syn1neg, int32_t n_local,
+                                 int32_t dim, uint32_t k0, uint32_t k1, int32_t part, int32_t n_parts)
 {
     const int32_t chunks = (dim + 3) >> 2;
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= (int64_t)V * chunks) return;
+    if (t >= (int64_t)n_local * chunks) return;
     const int32_t row = (int32_t)(t / chunks), c = (int32_t)(t % chunks);
-    const Philox4 r = philox4x32_10((uint32_t)row, (uint32_t)c, 0x53594E30u, 0u, k0, k1);
+    const Philox4 r = philox4x32_10((uint32_t)(row * n_parts + part), (uint32_t)c, 0x53594E30u, 0u, k0, k1);
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -157,13 +159,28 @@ __device__ __forceinline__ void apply_target(float4 *row2p, float4 (&row2)[NV], 
     }
 }
 
-template <int NV, bool ATOMIC>
-__device__ __forceinline__ void train_pair(float *__restrict__ syn0, float *__restrict__ syn1neg, int32_t dim,
+// Where the rows live. Flat: one [V, dim] table per side on this device. Sharded: row i of a table
+// lives in part i % n_parts (n_parts a power of two; parts may be peer-GPU memory mapped over
+// NVLink) at local row i / n_parts -- vocabulary order is count-descending, so the parts carry
+// equal shares of the traffic.
+struct RowsFlat {
+    float *s0, *s1; int32_t dim;
+    __device__ __forceinline__ float *r0(int32_t i) const { return s0 + (int64_t)i * dim; }
+    __device__ __forceinline__ float *r1(int32_t i) const { return s1 + (int64_t)i * dim; }
+};
+struct RowsSharded {
+    float *const *p0; float *const *p1; int32_t dim, lg, mask;      // p0/p1: 2 x n_parts pointers in shared memory
+    __device__ __forceinline__ float *r0(int32_t i) const { return p0[i & mask] + (int64_t)(i >> lg) * dim; }
+    __device__ __forceinline__ float *r1(int32_t i) const { return p1[i & mask] + (int64_t)(i >> lg) * dim; }
+};
+
+template <int NV, bool ATOMIC, class Rows>
+__device__ __forceinline__ void train_pair(const Rows rows, int32_t dim,
                                            int32_t centre, int32_t ctx, int32_t my_t, int32_t negative,
                                            float alpha, const bool (&act)[NV], const float *s_exp, int lane)
 {
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 *row1p = reinterpret_cast<float4 *>(syn0 + (int64_t)ctx * dim);
+    float4 *row1p = reinterpret_cast<float4 *>(rows.r0(ctx));
     float4 row1[NV], work[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) { row1[c] = act[c] ? row1p[c * 32 + lane] : zero4; work[c] = zero4; }
@@ -187,7 +204,7 @@ __device__ __forceinline__ void train_pair(float *__restrict__ syn0, float *__re
         float f[FN + 1];
 #pragma unroll
         for (int d = 0; d <= FN; ++d) {
-            const float4 *rp = reinterpret_cast<const float4 *>(syn1neg + (int64_t)tg[d] * dim);
+            const float4 *rp = reinterpret_cast<const float4 *>(rows.r1(tg[d]));
             r2[d][0] = (act[0] && !(d > 0 && tg[d] == centre)) ? rp[lane] : zero4;
         }
 #pragma unroll
@@ -203,7 +220,7 @@ __device__ __forceinline__ void train_pair(float *__restrict__ syn0, float *__re
             if (f[d] <= -(float)MAX_EXP || f[d] >= (float)MAX_EXP) continue;
             const float sg = s_exp[(int)((f[d] + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))];
             const float g = ((d == 0 ? 1.0f : 0.0f) - sg) * alpha;
-            float4 *row2p = reinterpret_cast<float4 *>(syn1neg + (int64_t)tg[d] * dim);
+            float4 *row2p = reinterpret_cast<float4 *>(rows.r1(tg[d]));
             apply_target<1, ATOMIC>(row2p, r2[d], reinterpret_cast<const float4 (&)[1]>(row1),
                                     reinterpret_cast<float4 (&)[1]>(work), g,
                                     reinterpret_cast<const bool (&)[1]>(act), lane);
@@ -217,7 +234,7 @@ __device__ __forceinline__ void train_pair(float *__restrict__ syn0, float *__re
                 if (target == centre) continue;
                 label = 0.0f;
             }
-            float4 *row2p = reinterpret_cast<float4 *>(syn1neg + (int64_t)target * dim);
+            float4 *row2p = reinterpret_cast<float4 *>(rows.r1(target));
             float4 row2[NV];
             float f = 0.0f;
 #pragma unroll
@@ -251,6 +268,7 @@ struct SgnsArgs {
     const uint32_t *keep_thr; const uint32_t *cum_table; const int32_t *bucket_lo;
     n2v_sgns_params_t p;
     float *syn0, *syn1neg; unsigned long long *pairs_out;
+    float *parts0[8], *parts1[8]; int32_t parts_log2;     // sharded tables (v3 only): n_parts = 1 << parts_log2
 };
 
 struct WarpSentence {       // per-warp staging of the kept tokens of one sentence chunk
@@ -385,7 +403,7 @@ sgns_train_kernel(SgnsArgs a)
                 for (; j < kend; ++j) {
                     if (j == i) continue;
                     const int32_t my_t = draw_pair_negatives(a, ws, i, j, gs, ep8, k0, k1, lane);
-                    train_pair<NV, ATOMIC>(a.syn0, a.syn1neg, dim, centre, ws.idx[j], my_t, negative, alpha, act, s_exp, lane);
+                    train_pair<NV, ATOMIC>(RowsFlat{a.syn0, a.syn1neg, dim}, dim, centre, ws.idx[j], my_t, negative, alpha, act, s_exp, lane);
                     ++pairs;
                 }
             }
@@ -574,7 +592,7 @@ sgns_train_kernel_v2(SgnsArgs a)
 #define N2V_V3_MINB 5
 #endif
 // FULL: dim == 128 exactly (every lane holds 4 floats of every row, no masking)
-template <bool ATOMIC, bool FULL>
+template <bool ATOMIC, bool FULL, bool SHARDED>
 __global__ void __launch_bounds__(SGNS_BLOCK, N2V_V3_MINB)
 sgns_train_kernel_v3(SgnsArgs a)
 {
@@ -586,7 +604,9 @@ sgns_train_kernel_v3(SgnsArgs a)
     // the carried rows as first read (one reduction of out - orig per row at the end of a centre):
     // parked in shared memory, each lane touches only its own 16 bytes -- keeps 24 registers free
     __shared__ float4 s_orig[SGNS_BLOCK / 32][FN + 1][32];
+    __shared__ float *s_parts[2][8];
     for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = exp_table_entry(i);
+    if (SHARDED && threadIdx.x < 16) s_parts[threadIdx.x >> 3][threadIdx.x & 7] = (threadIdx.x < 8 ? a.parts0 : a.parts1)[threadIdx.x & 7];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -599,7 +619,10 @@ sgns_train_kernel_v3(SgnsArgs a)
     const uint32_t ep8 = a.p.epoch << 8;
     const bool on = FULL || (lane * 4 < dim);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float *const syn0 = a.syn0, *const syn1neg = a.syn1neg;
+    using Rows = typename std::conditional<SHARDED, RowsSharded, RowsFlat>::type;
+    Rows rows;
+    if constexpr (SHARDED) rows = RowsSharded{s_parts[0], s_parts[1], dim, a.parts_log2, (1 << a.parts_log2) - 1};
+    else rows = RowsFlat{a.syn0, a.syn1neg, dim};
     unsigned long long pairs = 0, centres = 0;
 
     // lane n draws shared negative n of centre position i: Philox ctr (pos_i << 16 | 0xFFFF)
@@ -653,23 +676,23 @@ sgns_train_kernel_v3(SgnsArgs a)
                 if (!dup) {
                     float4 out[FN + 1];
                     uint32_t skipmask = 0xC0u;                 // padding targets 6, 7
-                    out[0] = on ? ldcg4(syn1neg + (int64_t)centre * dim, lane) : zero4;
+                    out[0] = on ? ldcg4(rows.r1(centre), lane) : zero4;
 #pragma unroll
                     for (int d = 0; d < FN; ++d)
-                        out[d + 1] = (on && tg[d] != centre) ? ldcg4(syn1neg + (int64_t)tg[d] * dim, lane) : zero4;
+                        out[d + 1] = (on && tg[d] != centre) ? ldcg4(rows.r1(tg[d]), lane) : zero4;
 #pragma unroll
                     for (int d = 0; d < FN; ++d) if (tg[d] == centre) skipmask |= 2u << d;   // skipped, not redrawn
 #pragma unroll
                     for (int d = 0; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
-                    float4 row1 = on ? ldcg4(syn0 + (int64_t)ws.idx[j] * dim, lane) : zero4;
+                    float4 row1 = on ? ldcg4(rows.r0(ws.idx[j]), lane) : zero4;
                     const int32_t t_nxt = ni < c_hi ? draw_centre(ni, gs) : -1;
                     if (ni < c_hi) {                       // next centre's output rows: L2 warm-up
-                        prefetch_row_l2(syn1neg + (int64_t)ws.idx[ni] * dim, lane);
+                        prefetch_row_l2(rows.r1(ws.idx[ni]), lane);
 #pragma unroll
                         for (int d = 0; d < FN; ++d) {
                             const int32_t tn = __shfl_sync(0xFFFFFFFFu, t_nxt, d);
-                            if (on) prefetch_row_l2(syn1neg + (int64_t)tn * dim, lane);
+                            if (on) prefetch_row_l2(rows.r1(tn), lane);
                         }
                     }
                     while (j < kend) {
@@ -679,7 +702,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                         // stale only if it is the very row this pair is about to update
                         const int32_t ctx_n = ws.idx[jn < kend ? jn : j];
                         const bool stale = ctx_n == ctx;
-                        const float4 row1n = on ? ldcg4(syn0 + (int64_t)ctx_n * dim, lane) : zero4;
+                        const float4 row1n = on ? ldcg4(rows.r0(ctx_n), lane) : zero4;
 
                         // 6 dot products, reduced by a transposing butterfly: after the rounds on lane
                         // bits 4,3,2 each lane holds ONE of the (padded) 8 sums, bits 1,0 finish it:
@@ -717,10 +740,10 @@ sgns_train_kernel_v3(SgnsArgs a)
                         }
                         float4 upd1 = row1;
                         upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
-                        add_row<ATOMIC>(syn0 + (int64_t)ctx * dim, lane, work, upd1, on);
+                        add_row<ATOMIC>(rows.r0(ctx), lane, work, upd1, on);
                         j = jn;
                         row1 = row1n;
-                        if (stale && j < kend) row1 = on ? ldcg4(syn0 + (int64_t)ctx * dim, lane) : zero4;   // re-read after the update
+                        if (stale && j < kend) row1 = on ? ldcg4(rows.r0(ctx), lane) : zero4;   // re-read after the update
                     }
                     pairs += (unsigned long long)(kend - j0 - ((i >= j0 && i < kend) ? 1 : 0));
                     // one reduction per carried row: what this centre's pairs added to it
@@ -729,7 +752,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                         if ((skipmask >> d) & 1u) continue;
                         const float4 og = s_orig[wib][d][lane];
                         const float4 dl = make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w);
-                        add_row<ATOMIC>(syn1neg + (int64_t)(d == 0 ? centre : tg[d - 1]) * dim, lane, dl, out[d], on);
+                        add_row<ATOMIC>(rows.r1(d == 0 ? centre : tg[d - 1]), lane, dl, out[d], on);
                     }
                     t_cur = t_nxt;
                 } else {
@@ -738,7 +761,7 @@ sgns_train_kernel_v3(SgnsArgs a)
                     const bool act1[1] = {on};
                     for (int32_t j = j0; j < kend; ++j) {
                         if (j == i) continue;
-                        train_pair<1, ATOMIC>(syn0, syn1neg, dim, centre, ws.idx[j], t_cur, FN, alpha, act1, s_exp, lane);
+                        train_pair<1, ATOMIC>(rows, dim, centre, ws.idx[j], t_cur, FN, alpha, act1, s_exp, lane);
                         ++pairs;
                     }
                     t_cur = t_nxt;
@@ -844,24 +867,39 @@ extern "C" int n2v_sgns_init(float *syn0, float *syn1neg, int32_t V, int32_t dim
     if (V == 0) return N2V_OK;
     N2V_REQUIRE(syn0, "syn0 is NULL");
     const int64_t n = (int64_t)V * ((dim + 3) >> 2);
-    sgns_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(syn0, syn1neg, V, dim, (uint32_t)seed, (uint32_t)(seed >> 32));
+    sgns_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(syn0, syn1neg, V, dim, (uint32_t)seed, (uint32_t)(seed >> 32), 0, 1);
     N2V_LAUNCH_CHECK();
     return N2V_OK;
 }
 
-extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
-                              int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
-                              const uint32_t *keep_thr, const uint32_t *cum_table,
-                              const int32_t *bucket_lo, const n2v_sgns_params_t *params,
-                              float *syn0, float *syn1neg, unsigned long long *pairs_out,
-                              void *stream_)
+extern "C" int n2v_sgns_init_part(float *syn0_part, float *syn1neg_part, int32_t V, int32_t dim, uint64_t seed,
+                                  int32_t part, int32_t n_parts, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    N2V_REQUIRE(V >= 0 && dim > 0 && n_parts >= 1 && part >= 0 && part < n_parts, "bad size");
+    const int32_t n_local = (V - part + n_parts - 1) / n_parts;
+    if (n_local <= 0) return N2V_OK;
+    N2V_REQUIRE(syn0_part, "syn0_part is NULL");
+    const int64_t n = (int64_t)n_local * ((dim + 3) >> 2);
+    sgns_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(syn0_part, syn1neg_part, n_local, dim, (uint32_t)seed,
+                                                                      (uint32_t)(seed >> 32), part, n_parts);
+    N2V_LAUNCH_CHECK();
+    return N2V_OK;
+}
+
+static int sgns_train_impl(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                           int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                           const uint32_t *keep_thr, const uint32_t *cum_table,
+                           const int32_t *bucket_lo, const n2v_sgns_params_t *params,
+                           float *syn0, float *syn1neg, float *const *parts0, float *const *parts1, int n_parts,
+                           unsigned long long *pairs_out, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     N2V_REQUIRE(params, "params is NULL");
     N2V_REQUIRE(n_sent >= 0, "negative n_sent");
     if (n_sent == 0) return N2V_OK;
     const n2v_sgns_params_t &p = *params;
-    N2V_REQUIRE(tokens && cum_table && bucket_lo && syn0 && syn1neg, "NULL buffer");
+    N2V_REQUIRE(tokens && cum_table && bucket_lo && (n_parts > 0 || (syn0 && syn1neg)), "NULL buffer");
     N2V_REQUIRE(sent_off || stride > 0, "need sent_off or a positive stride");
     N2V_REQUIRE(p.V > 0 && p.dim > 0 && p.dim % 4 == 0 && p.dim <= 1024, "dim must be a multiple of 4, <= 1024");
     N2V_REQUIRE(p.window >= 1 && p.window <= 96, "window out of range (1..96)");
@@ -871,17 +909,31 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
     N2V_REQUIRE(p.bucket_bits >= 1 && p.bucket_bits <= 24, "bucket_bits out of range");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
     SgnsArgs a{tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table,
-               bucket_lo, p, syn0, syn1neg, pairs_out};
+               bucket_lo, p, syn0, syn1neg, pairs_out, {}, {}, -1};
+    if (n_parts > 0) {
+        N2V_REQUIRE(n_parts <= 8 && (n_parts & (n_parts - 1)) == 0 && parts0 && parts1, "n_parts must be 1, 2, 4 or 8");
+        N2V_REQUIRE(p.negative_sharing && p.dim <= 128 && p.negative == 5, "sharded tables: shared-negative kernel only");
+        for (int i = 0; i < n_parts; ++i) {
+            N2V_REQUIRE(parts0[i] && parts1[i], "NULL table part");
+            a.parts0[i] = parts0[i]; a.parts1[i] = parts1[i];
+        }
+        a.parts_log2 = 0;
+        while ((1 << a.parts_log2) < n_parts) ++a.parts_log2;
+    }
     const int nv = (p.dim + 127) / 128;
     if (p.negative_sharing) {
         N2V_REQUIRE(nv == 1 && p.negative == 5, "negative_sharing needs dim <= 128 and negative == 5");
         const int blocks = (p.grid_warps + SGNS_BLOCK / 32 - 1) / (SGNS_BLOCK / 32);
-        if (p.dim == 128) {
-            if (p.atomic_updates) sgns_train_kernel_v3<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
-            else sgns_train_kernel_v3<false, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        if (a.parts_log2 >= 0) {
+            N2V_REQUIRE(p.atomic_updates, "sharded tables need atomic updates");
+            if (p.dim == 128) sgns_train_kernel_v3<true, true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            else sgns_train_kernel_v3<true, false, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        } else if (p.dim == 128) {
+            if (p.atomic_updates) sgns_train_kernel_v3<true, true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            else sgns_train_kernel_v3<false, true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         } else {
-            if (p.atomic_updates) sgns_train_kernel_v3<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
-            else sgns_train_kernel_v3<false, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            if (p.atomic_updates) sgns_train_kernel_v3<true, false, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+            else sgns_train_kernel_v3<false, false, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         }
         N2V_LAUNCH_CHECK();
         return N2V_OK;
@@ -900,4 +952,26 @@ extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, in
         case 4: return launch_train<4>(a, stream);
         default: return launch_train<8>(a, stream);
     }
+}
+
+extern "C" int n2v_sgns_train(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                              int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                              const uint32_t *keep_thr, const uint32_t *cum_table,
+                              const int32_t *bucket_lo, const n2v_sgns_params_t *params,
+                              float *syn0, float *syn1neg, unsigned long long *pairs_out,
+                              void *stream)
+{
+    return sgns_train_impl(tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table, bucket_lo,
+                           params, syn0, syn1neg, nullptr, nullptr, 0, pairs_out, stream);
+}
+
+extern "C" int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent,
+                                      int32_t stride, int64_t sent_id_base, const int32_t *vocab_of_id,
+                                      const uint32_t *keep_thr, const uint32_t *cum_table,
+                                      const int32_t *bucket_lo, const n2v_sgns_params_t *params,
+                                      float *const *syn0_parts, float *const *syn1neg_parts, int32_t n_parts,
+                                      unsigned long long *pairs_out, void *stream)
+{
+    return sgns_train_impl(tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, cum_table, bucket_lo,
+                           params, nullptr, nullptr, syn0_parts, syn1neg_parts, n_parts, pairs_out, stream);
 }

@@ -82,3 +82,39 @@ def average_tables(*tables: torch.Tensor):
     for t in tables:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         t.mul_(1.0 / w)
+
+
+# ---- one logical table pair across the GPUs of a node (peer memory over NVLink) -------------------
+def _ipc_export(t: torch.Tensor):
+    """(ipc handle bytes, byte offset of t inside its cudaMalloc block)"""
+    from cuda.bindings import driver as cu, runtime as cudart
+    err, h = cudart.cudaIpcGetMemHandle(t.data_ptr())
+    if int(err) != 0:
+        raise RuntimeError("cudaIpcGetMemHandle failed: %s" % err)
+    err, base, _size = cu.cuMemGetAddressRange(t.data_ptr())
+    if int(err) != 0:
+        raise RuntimeError("cuMemGetAddressRange failed: %s" % err)
+    return bytes(bytearray(h.reserved)), int(t.data_ptr()) - int(base)
+
+
+def _ipc_import(handle: bytes, offset: int) -> int:
+    from cuda.bindings import runtime as cudart
+    h = cudart.cudaIpcMemHandle_t()
+    h.reserved = list(handle)
+    err, ptr = cudart.cudaIpcOpenMemHandle(h, cudart.cudaIpcMemLazyEnablePeerAccess)
+    if int(err) != 0:
+        raise RuntimeError("cudaIpcOpenMemHandle failed: %s" % err)
+    return int(ptr) + offset
+
+
+def exchange_peer_pointers(local: torch.Tensor):
+    """Every rank contributes one device tensor; returns the list of world device addresses at
+    which THIS rank can read/write rank r's tensor (its own for r == rank, NVLink peer mappings
+    otherwise). The tensors must stay alive until every rank is done with them."""
+    rank, w = world()
+    if w == 1:
+        return [int(local.data_ptr())]
+    mine = _ipc_export(local)
+    everyone = [None] * w
+    dist.all_gather_object(everyone, mine)
+    return [int(local.data_ptr()) if r == rank else _ipc_import(*everyone[r]) for r in range(w)]

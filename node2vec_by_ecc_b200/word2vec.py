@@ -266,6 +266,91 @@ class SgnsTrainer:
                                    ptr(self.pairs), stream()))
 
 
+class PeerSgnsTrainer(SgnsTrainer):
+    """SgnsTrainer whose syn0 / syn1neg are ONE logical pair of tables spread over `n_parts`
+    allocations: vocabulary row i lives in part i % n_parts at local row i // n_parts
+    (n2v_sgns_train_sharded). Two uses:
+      * multi-GPU (one process per GPU, torch.distributed initialised): every rank allocates its own
+        part, the parts are mapped into every process over NVLink (CUDA IPC), and all ranks train
+        their own walks against the same tables -- gensim's shared-memory Hogwild across GPUs; no
+        replicas, so nothing to average (dist.py explains why replicas do not survive sparse sync);
+      * single process with `local_parts` > 1: all parts on this device (tests the addressing)."""
+
+    def __init__(self, counts_by_id, *args, local_parts: int = 0, **kw):
+        from . import dist as D
+        self._rank, self._world = D.world()
+        self._local_parts = int(local_parts)
+        self.n_parts = self._local_parts if self._local_parts else self._world
+        if self.n_parts not in (1, 2, 4, 8):
+            raise ValueError("the tables can be spread over 1, 2, 4 or 8 parts")
+        super().__init__(counts_by_id, *args, **kw)
+
+    def reset_weights(self):
+        from . import dist as D
+        dev = self.counts.device
+        W = self.n_parts
+        mine = range(W) if self._local_parts else [self._rank]
+        self.parts0, self.parts1 = {}, {}
+        for k in mine:
+            n_local = max((self.V - k + W - 1) // W, 1)
+            self.parts0[k] = torch.empty((n_local, self.dim), dtype=torch.float32, device=dev)
+            self.parts1[k] = torch.empty((n_local, self.dim), dtype=torch.float32, device=dev)
+            check(lib().n2v_sgns_init_part(ptr(self.parts0[k]), ptr(self.parts1[k]), C.c_int32(self.V), C.c_int32(self.dim),
+                                           C.c_uint64(self.seed), C.c_int32(k), C.c_int32(W), stream()))
+        torch.cuda.synchronize()
+        if self._local_parts:
+            a0 = [self.parts0[k].data_ptr() for k in range(W)]
+            a1 = [self.parts1[k].data_ptr() for k in range(W)]
+        else:
+            a0 = D.exchange_peer_pointers(self.parts0[self._rank])
+            a1 = D.exchange_peer_pointers(self.parts1[self._rank])
+        self._p0 = (C.c_void_p * W)(*a0)
+        self._p1 = (C.c_void_p * W)(*a1)
+        self.syn0 = self.syn1neg = None
+
+    def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
+              epoch=0, sent_per_job=125, grid_warps=None, atomic_updates=1, alpha=None, min_alpha=None,
+              tuning=None, negative_sharing=1):
+        if not negative_sharing or self.dim > 128 or self.negative != 5:
+            raise NotImplementedError("sharded tables run the shared-negative kernel (dim <= 128, negative = 5)")
+        P = SgnsParams()
+        P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
+        P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
+        P.alpha0 = self.alpha if alpha is None else float(alpha)
+        P.min_alpha = self.min_alpha if min_alpha is None else float(min_alpha)
+        P.total_examples, P.example_base = int(total_examples), int(example_base)
+        P.sent_per_job = max(1, int(sent_per_job))
+        P.epoch, P.seed = int(epoch), self.seed
+        P.grid_warps = int(grid_warps or self.default_hogwild_warps(True))
+        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
+        check(lib().n2v_sgns_train_sharded(ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride),
+                                           C.c_int64(sent_id_base), ptr(self.vocab_of_id),
+                                           ptr(self.keep_thr if self.sample > 0 else None), ptr(self.cum_table),
+                                           ptr(self.bucket_lo), C.byref(P), self._p0, self._p1, C.c_int32(self.n_parts),
+                                           ptr(self.pairs), stream()))
+
+    def gather(self):
+        """-> (syn0, syn1neg) float32[V, dim] on this device, rows in vocabulary order"""
+        import torch.distributed as tdist
+        W, dev = self.n_parts, self.counts.device
+        out = []
+        for parts in (self.parts0, self.parts1):
+            full = torch.empty((self.V, self.dim), dtype=torch.float32, device=dev)
+            if self._local_parts or W == 1:
+                got = [parts[k] for k in sorted(parts)]
+            else:
+                n0 = (self.V + W - 1) // W
+                mine = torch.zeros((n0, self.dim), dtype=torch.float32, device=dev)
+                mine[: parts[self._rank].shape[0]] = parts[self._rank]
+                got = [torch.empty_like(mine) for _ in range(W)]
+                tdist.all_gather(got, mine)
+            for k in range(W):
+                rows = (self.V - k + W - 1) // W
+                full[k::W] = got[k][:rows]
+            out.append(full)
+        return out[0], out[1]
+
+
 class Word2Vec:
     """gensim.models.Word2Vec(sg=1, hs=0, negative=k) on the GPU. Signature and defaults are
     gensim 3.2.0's; the reference passes size, window, min_count=0, sg=1, workers, iter."""

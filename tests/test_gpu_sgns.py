@@ -222,3 +222,28 @@ def test_long_ragged_sentences_stream_with_exact_windows(shared, negative):
                                       rng_mode=3 if shared else 1, seed=2)
     assert m.pairs_trained == pairs and pairs > 20000
     assert np.abs(m.wv.syn0 - s0).max() < 2e-4 and np.abs(m.syn1neg_dev.cpu().numpy() - s1).max() < 2e-4
+
+
+@pytest.mark.parametrize("n_parts,size", [(2, 128), (4, 64), (8, 128)])
+def test_sharded_tables_sequential_equal_oracle(n_parts, size):
+    """n2v_sgns_train_sharded: the same tables spread over n_parts allocations (row i in part
+    i % n_parts) -- here all on one device; sequential run == the oracle's shared mode."""
+    from node2vec_by_ecc_b200 import PeerSgnsTrainer
+    z, g, corpus = corpus_from_golden("karate_p025_q4")
+    walks = corpus.walks
+    counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=g.n)
+    tr = PeerSgnsTrainer(counts, dim=size, window=10, negative=5, sample=1e-3, seed=4, local_parts=n_parts)
+    tr.train(walks, None, walks.shape[0], walks.shape[1], total_examples=walks.shape[0], sent_per_job=125, grid_warps=1)
+    s0_dev, s1_dev = tr.gather()
+    order = tr.order.cpu().numpy()
+    id2index = np.full(g.n, -1, dtype=np.int32); id2index[order] = np.arange(len(order), dtype=np.int32)
+    keep = tr.keep_thr.cpu().numpy().view(np.uint32).astype(np.uint64)
+    keep = np.where(keep == 0xFFFFFFFF, np.uint64(1) << np.uint64(32), keep)
+    voc = oracle.Vocab(tr.counts.cpu().numpy(), order.astype(np.int32), id2index, keep,
+                       tr.cum_table.cpu().numpy().view(np.uint32).copy())
+    wn = z["walks"]
+    tok = np.where(wn >= 0, id2index[np.maximum(wn, 0)], -1).astype(np.int32)
+    off = np.arange(wn.shape[0] + 1, dtype=np.int64) * wn.shape[1]
+    s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=size, window=10, negative=5, iters=1, workers=1, rng_mode=3, seed=4)
+    assert int(tr.pairs[0]) == pairs
+    assert np.abs(s0_dev.cpu().numpy() - s0).max() < 2e-4 and np.abs(s1_dev.cpu().numpy() - s1).max() < 2e-4
