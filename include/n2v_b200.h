@@ -217,6 +217,40 @@ int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64
                            float *const *syn1neg_parts, int32_t n_parts,
                            unsigned long long *pairs_out, void *stream);
 
+/* Block-partitioned training (the multi-GPU form of learn_embeddings, src/main.py:82-90; same
+ * per-pair arithmetic as n2v_sgns_train). Tables in n_parts row sets as above. A pool of walks is
+ * expanded into (centre, context) pairs; the pairs whose centre is in part `part` are written as
+ * n_parts streams, stream b = pairs whose context is in part b, each pair int32 {centre local row,
+ * context local row}. Stream (part, b) touches only syn1neg part `part` and syn0 part b, so GPU k
+ * trains stream (k, (k + e) % n_parts) in sub-step e and the syn0 parts travel round a ring: no row
+ * is replicated, nothing is averaged.
+ *   n2v_sgns_pairs_count: offsets int64[n_parts * n_sent + 1], exclusive scan of the per-(stream,
+ *       sentence) pair counts in stream-major order: stream b = pairs [offsets[b * n_sent],
+ *       offsets[(b + 1) * n_sent]); the last entry is the total.
+ *   n2v_sgns_pairs_fill: writes the pairs (order: stream, sentence, centre, context); pairs beyond
+ *       capacity_pairs are dropped and counted in *overflow (device uint64).
+ *   n2v_sgns_train_block: trains pairs[0, n_pairs) of one stream against (syn0 part of the stream's
+ *       contexts, syn1neg part `part`). One set of 5 negatives per run of run_pairs (<= 32)
+ *       consecutive pairs, Philox ctr (run, tag, epoch), each draw mapped to the word of the same
+ *       local row in `part`; a row repeated in the set is used once, a negative equal to a pair's
+ *       centre is skipped for that pair. alpha is the caller's (one value per call). Uses params->
+ *       V, dim (<= 128), negative (5), bucket_bits, seed, epoch, grid_warps, atomic_updates.
+ *       pairs_out[0] += pairs, [1] += runs. */
+size_t n2v_sgns_pairs_workspace_bytes(int64_t n_sent, int32_t n_parts);
+int n2v_sgns_pairs_count(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
+                         int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
+                         const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
+                         int64_t *offsets, void *workspace, size_t workspace_bytes, void *stream);
+int n2v_sgns_pairs_fill(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
+                        int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
+                        const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
+                        const int64_t *offsets, int32_t *pairs, int64_t capacity_pairs,
+                        unsigned long long *overflow, void *stream);
+int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const uint32_t *cum_table,
+                         const int32_t *bucket_lo, const n2v_sgns_params_t *params, float alpha,
+                         int32_t run_pairs, uint32_t tag, float *syn0_part, float *syn1neg_part,
+                         int32_t part, int32_t n_parts, unsigned long long *pairs_out, void *stream);
+
 /* ---- link scoring ---------------------------------------------------------------------------
  * replaces: link_score(emb, a, b) with link_method "cos" (src/main_link.py:43-49) over a batch of
  * pairs, as looped by get_roc_score (:173-189). a/b: row indices (-1 = word not in vocabulary ->

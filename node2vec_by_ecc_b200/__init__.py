@@ -8,7 +8,7 @@ There is no CPU fallback: without the library or a CUDA device every compute cal
 from ._lib import N2VError, SO_PATH, lib  # noqa: F401
 from .graph import AliasTables, DeviceGraph  # noqa: F401
 from .walker import Graph, WalkCorpus, alias_draw, alias_setup  # noqa: F401
-from .word2vec import KeyedVectors, LineSentence, PeerSgnsTrainer, SgnsTrainer, Vocab, Word2Vec  # noqa: F401
+from .word2vec import BlockSgnsTrainer, KeyedVectors, LineSentence, PeerSgnsTrainer, SgnsTrainer, Vocab, Word2Vec  # noqa: F401
 
 __all__ = ["Graph", "WalkCorpus", "alias_setup", "alias_draw", "DeviceGraph", "AliasTables",
            "Word2Vec", "KeyedVectors", "LineSentence", "Vocab", "N2VError", "lib", "SO_PATH"]

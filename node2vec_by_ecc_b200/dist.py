@@ -118,3 +118,33 @@ def exchange_peer_pointers(local: torch.Tensor):
     everyone = [None] * w
     dist.all_gather_object(everyone, mine)
     return [int(local.data_ptr()) if r == rank else _ipc_import(*everyone[r]) for r in range(w)]
+
+
+# ---- block-partitioned SGNS (word2vec.BlockSgnsTrainer) --------------------------------------------
+def bucket_of(rank: int, sub_step: int, world_size: int) -> int:
+    """the syn0 part rank `rank` holds -- and the pair bucket it trains -- in sub-step `sub_step`"""
+    return (rank + sub_step) % world_size
+
+
+def gather_pool(local_walks: torch.Tensor) -> torch.Tensor:
+    """every rank's [n, stride] walk buffer -> the pool [world * n, stride] in rank order"""
+    rank, w = world()
+    if w == 1:
+        return local_walks
+    local_walks = local_walks.contiguous()
+    pool = torch.empty((w * local_walks.shape[0],) + tuple(local_walks.shape[1:]), dtype=local_walks.dtype,
+                       device=local_walks.device)
+    dist.all_gather_into_tensor(pool, local_walks)
+    return pool
+
+
+def ring_pass(held: torch.Tensor, spare: torch.Tensor):
+    """hand `held` to rank - 1 and receive rank + 1's into `spare`; -> (new held, new spare).
+    After world_size passes every part is back where it started."""
+    rank, w = world()
+    if w == 1:
+        return held, spare
+    ops = [dist.P2POp(dist.isend, held, (rank - 1) % w), dist.P2POp(dist.irecv, spare, (rank + 1) % w)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return spare, held

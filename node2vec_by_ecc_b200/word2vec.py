@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch
 
-from ._lib import SgnsParams, check, lib, ptr, require_cuda, stream
+from ._lib import N2VError, SgnsParams, check, lib, ptr, require_cuda, stream
 from .walker import WalkCorpus
 
 
@@ -344,6 +344,160 @@ class PeerSgnsTrainer(SgnsTrainer):
                 mine[: parts[self._rank].shape[0]] = parts[self._rank]
                 got = [torch.empty_like(mine) for _ in range(W)]
                 tdist.all_gather(got, mine)
+            for k in range(W):
+                rows = (self.V - k + W - 1) // W
+                full[k::W] = got[k][:rows]
+            out.append(full)
+        return out[0], out[1]
+
+
+class BlockSgnsTrainer(SgnsTrainer):
+    """Block-partitioned SGNS: the multi-GPU trainer (csrc/n2v_sgns_block.cu).
+
+    syn0 / syn1neg are cut into n_parts row sets (vocabulary row i -> part i % n_parts). Every
+    train() call is one POOL of walks: its (centre, context) pairs are bucketed by (part of the
+    centre, part of the context); bucket (k, b) touches only syn1neg part k and syn0 part b. GPU k
+    keeps syn1neg part k, trains bucket (k, (k + e) % n) in sub-step e and hands the syn0 part it
+    holds to GPU k - 1 between sub-steps (dist.ring_pass). No replicas, nothing to average, every
+    row has one writer GPU at a time.
+      * one process per GPU (torch.distributed initialised): n_parts = world size; every rank calls
+        train() with ITS walks [n_sent, stride] of the pool; the pool is rank 0's walks, then rank
+        1's, ... (all-gathered, 4 bytes per token), sentence ids sent_id_base + position in pool;
+      * single process, local_parts = n: all parts on this device, buckets run in the order the n
+        GPUs would run them (the exact emulation the parity and AUC tests use; n = 1 is a plain
+        single-GPU trainer over a pair stream).
+    alpha is fixed per pool: alpha0 - (alpha0 - min_alpha) * example_base / total_examples."""
+
+    def __init__(self, counts_by_id, *args, local_parts: int = 0, run_pairs: int = 16, **kw):
+        from . import dist as D
+        self._rank, self._world = D.world()
+        self._local_parts = int(local_parts)
+        self.n_parts = self._local_parts if self._local_parts else self._world
+        if self.n_parts not in (1, 2, 4, 8):
+            raise ValueError("the tables can be cut into 1, 2, 4 or 8 parts")
+        self.run_pairs = int(run_pairs)
+        self._pool = 0
+        self._buf = {}
+        super().__init__(counts_by_id, *args, **kw)
+        if self.V < self.n_parts:
+            raise ValueError("fewer vocabulary rows than parts")
+
+    @property
+    def _mine(self):
+        return range(self.n_parts) if self._local_parts else [self._rank]
+
+    def reset_weights(self):
+        dev = self.counts.device
+        W = self.n_parts
+        rows = (self.V + W - 1) // W                    # same shape for every part: ring buffers interchange
+        self.parts0, self.parts1 = {}, {}
+        for k in self._mine:
+            self.parts0[k] = torch.zeros((rows, self.dim), dtype=torch.float32, device=dev)
+            self.parts1[k] = torch.zeros((rows, self.dim), dtype=torch.float32, device=dev)
+            check(lib().n2v_sgns_init_part(ptr(self.parts0[k]), ptr(self.parts1[k]), C.c_int32(self.V), C.c_int32(self.dim),
+                                           C.c_uint64(self.seed), C.c_int32(k), C.c_int32(W), stream()))
+        self._spare = torch.empty_like(self.parts0[self._rank]) if (not self._local_parts and W > 1) else None
+        self.syn0 = self.syn1neg = None
+
+    def default_hogwild_warps(self, shared: bool = True) -> int:
+        sms = int(lib().n2v_sm_count())
+        return int(max(4, min(sms * 20, (self.V // self.n_parts) // 4)))
+
+    def pool_alpha(self, example_base: int, total_examples: int, alpha=None, min_alpha=None) -> float:
+        a0 = self.alpha if alpha is None else float(alpha)
+        m = self.min_alpha if min_alpha is None else float(min_alpha)
+        return float(np.float32(max(m, a0 - (a0 - m) * (float(example_base) / float(max(1, total_examples))))))
+
+    def _params(self, epoch, grid_warps):
+        P = SgnsParams()
+        P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
+        P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
+        P.alpha0, P.min_alpha, P.total_examples, P.example_base, P.sent_per_job = self.alpha, self.min_alpha, 1, 0, 1
+        P.epoch, P.seed = int(epoch), self.seed
+        P.grid_warps = int(grid_warps or self.default_hogwild_warps())
+        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
+        return P
+
+    def make_pairs(self, tokens, sent_off, n_sent, stride, sent_id_base, P, part):
+        """-> (pairs int32[total, 2], bounds): stream b of `part` = pairs[bounds[b]:bounds[b + 1]]"""
+        dev, W = self.counts.device, self.n_parts
+        b = self._buf.setdefault(part, {})
+        n_off = W * n_sent + 1
+        if b.get("n_off", 0) < n_off:
+            b["offsets"] = torch.empty(n_off, dtype=torch.int64, device=dev)
+            b["ws"] = torch.empty(int(lib().n2v_sgns_pairs_workspace_bytes(C.c_int64(n_sent), C.c_int32(W))),
+                                  dtype=torch.uint8, device=dev)
+            b["n_off"] = n_off
+            b["overflow"] = torch.zeros(1, dtype=torch.int64, device=dev)
+        keep = ptr(self.keep_thr if self.sample > 0 else None)
+        head = (ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride), C.c_int64(sent_id_base),
+                ptr(self.vocab_of_id), keep, C.byref(P), C.c_int32(part), C.c_int32(W))
+        check(lib().n2v_sgns_pairs_count(*head, ptr(b["offsets"]), ptr(b["ws"]), C.c_size_t(b["ws"].numel()), stream()))
+        bounds = [int(x) for x in b["offsets"][: n_off : n_sent].cpu().tolist()]     # one small D2H read per pool
+        total = bounds[-1]
+        if b.get("cap", -1) < total:
+            b["cap"] = int(total * 1.1) + 1024
+            b["pairs"] = torch.empty((b["cap"], 2), dtype=torch.int32, device=dev)
+        check(lib().n2v_sgns_pairs_fill(*head, ptr(b["offsets"]), ptr(b["pairs"]), C.c_int64(b["cap"]),
+                                        ptr(b["overflow"]), stream()))
+        return b["pairs"], bounds
+
+    def train_bucket(self, pairs, first, n, syn0_part, part, bucket, P, alpha):
+        if n <= 0:
+            return
+        tag = (self._pool * 64 + part * 8 + bucket) & 0xFFFFFFFF
+        check(lib().n2v_sgns_train_block(C.c_void_p(pairs.data_ptr() + 8 * first), C.c_int64(n), ptr(self.cum_table),
+                                         ptr(self.bucket_lo), C.byref(P), C.c_float(alpha), C.c_int32(self.run_pairs),
+                                         C.c_uint32(tag), ptr(syn0_part), ptr(self.parts1[part]), C.c_int32(part),
+                                         C.c_int32(self.n_parts), ptr(self.pairs), stream()))
+
+    def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
+              epoch=0, grid_warps=None, alpha=None, min_alpha=None, **_ignored):
+        """One pool. Multi-GPU: every rank passes its own walks (fixed-stride buffer, same n_sent on
+        every rank) and the POOL's example_base / sent_id_base (identical on all ranks)."""
+        from . import dist as D
+        W = self.n_parts
+        multi = not self._local_parts and W > 1
+        if multi:
+            if sent_off is not None:
+                raise NotImplementedError("multi-GPU pools are fixed-stride walk buffers")
+            tokens = D.gather_pool(tokens[:n_sent])
+            n_sent = n_sent * W
+        if n_sent <= 0:
+            return
+        P = self._params(epoch, grid_warps)
+        al = self.pool_alpha(example_base, total_examples, alpha, min_alpha)
+        streams = {k: self.make_pairs(tokens, sent_off, n_sent, stride, sent_id_base, P, k) for k in self._mine}
+        held = None if self._local_parts else self.parts0[self._rank]
+        for e in range(W):
+            for k in self._mine:
+                b = (k + e) % W
+                pairs, bounds = streams[k]
+                self.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b],
+                                  self.parts0[b] if self._local_parts else held, k, b, P, al)
+            if multi:                                    # the syn0 part moves on; after W passes it is home again
+                held, self._spare = D.ring_pass(held, self._spare)
+        if multi:
+            self.parts0[self._rank] = held
+        self._pool += 1
+
+    def check_overflow(self):
+        for b in self._buf.values():
+            if int(b["overflow"].item()):
+                raise N2VError("pair buffer overflow (internal sizing error)")
+
+    def gather(self):
+        """-> (syn0, syn1neg) float32[V, dim] on this device, rows in vocabulary order"""
+        import torch.distributed as tdist
+        W, dev = self.n_parts, self.counts.device
+        out = []
+        for parts in (self.parts0, self.parts1):
+            full = torch.empty((self.V, self.dim), dtype=torch.float32, device=dev)
+            if self._local_parts or W == 1:
+                got = [parts[k] for k in sorted(parts)]
+            else:
+                got = [torch.empty_like(parts[self._rank]) for _ in range(W)]
+                tdist.all_gather(got, parts[self._rank].contiguous())
             for k in range(W):
                 rows = (self.V - k + W - 1) // W
                 full[k::W] = got[k][:rows]

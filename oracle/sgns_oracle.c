@@ -379,3 +379,131 @@ int sgns_oracle_train(const int32_t *tok, const int64_t *sent_off, int64_t n_sen
     free(jb); free(je); free(ja);
     return 0;
 }
+
+/* ---- block-partitioned training (csrc/n2v_sgns_block.cu) --------------------------------------
+ * Not gensim's schedule: the multi-GPU form of the same per-pair arithmetic. Tables cut into
+ * n_parts = 1 << lg row sets (row i -> part i % n_parts, local row i / n_parts).
+ *
+ * sgns_oracle_make_pairs: the (centre, context) pairs of the sentences whose centre lies in `part`,
+ * sub-sampling and window shrink addressed by Philox exactly as rng_mode bit 0 above, written as
+ * n_parts streams (stream b = context in part b) in the order sentence, centre, context. Two
+ * calls: pairs == NULL counts (stream_len[b]), then fill with stream_off[b] = start of stream b. */
+int sgns_oracle_make_pairs(const int32_t *tok, const int64_t *sent_off, int64_t n_sent, int64_t sent_id_base,
+                           int32_t window, const uint64_t *sample_int, uint64_t seed, uint32_t epoch,
+                           int32_t part, int32_t lg, int64_t *stream_len, const int64_t *stream_off,
+                           int32_t *pairs)
+{
+    const int32_t n_parts = 1 << lg, mask = n_parts - 1;
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
+    int32_t *red = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
+    int64_t cur[64];
+    if (!idx || !red) { free(idx); free(red); return -1; }
+    for (int32_t b = 0; b < n_parts; ++b) cur[b] = pairs ? stream_off[b] : 0;
+    for (int64_t s = 0; s < n_sent; ++s) {
+        const uint64_t gs = (uint64_t)(sent_id_base + s);
+        const int64_t b0 = sent_off[s], e0 = sent_off[s + 1];
+        int64_t n = 0;
+        for (int64_t t = b0; t < e0 && t - b0 < MAX_SENTENCE_LEN; ++t) {
+            const int32_t w = tok[t];
+            if (w < 0) continue;
+            uint32_t r[4]; philox_words(seed, gs, (uint32_t)(t - b0), epoch << 8, r);
+            if (sample_int && sample_int[w] < (uint64_t)r[0]) continue;
+            idx[n] = w; red[n] = (int32_t)(r[1] % (uint32_t)window); ++n;
+        }
+        for (int64_t i = 0; i < n; ++i) {
+            if ((idx[i] & mask) != part) continue;
+            int64_t j = i - window + red[i]; if (j < 0) j = 0;
+            int64_t k = i + window + 1 - red[i]; if (k > n) k = n;
+            for (; j < k; ++j) {
+                if (j == i) continue;
+                const int32_t b = idx[j] & mask;
+                if (pairs) { pairs[2 * cur[b]] = idx[i] >> lg; pairs[2 * cur[b] + 1] = idx[j] >> lg; }
+                ++cur[b];
+            }
+        }
+    }
+    if (!pairs) for (int32_t b = 0; b < n_parts; ++b) stream_len[b] = cur[b];
+    free(idx); free(red);
+    return 0;
+}
+
+/* sgns_oracle_block_train: one stream against (syn0 part, syn1neg part `part`). One negative set
+ * per run of K consecutive pairs: Philox ctr (run lo, run hi, tag, epoch << 8 | 1 + n / 4), draw
+ * mapped to the word of the same local row in `part`; a row repeated in the set is used once; the
+ * centre row and the set are worked on in private copies for the run and written back as
+ * (copy - first read), which is what the device's carried registers + reductions do. */
+int sgns_oracle_block_train(const int32_t *pairs, int64_t n_pairs, float *syn0_part, float *syn1_part,
+                            int32_t part, int32_t lg, int32_t V, int32_t dim, const uint32_t *cum_table,
+                            float alpha, int32_t K, uint64_t seed, uint32_t epoch, uint32_t tag)
+{
+    pthread_once(&exp_once, build_exp_table);
+    enum { FN = 5 };
+    float *out = (float *)malloc(sizeof(float) * (size_t)dim * (FN + 1) * 2 + sizeof(float) * (size_t)dim);
+    if (!out) return -1;
+    float *orig = out + (size_t)dim * (FN + 1), *work = orig + (size_t)dim * (FN + 1);
+    const uint32_t cum_last = cum_table[V - 1];
+    const int64_t n_runs = (n_pairs + K - 1) / K;
+    for (int64_t run = 0; run < n_runs; ++run) {
+        int32_t tg[FN]; int skip_base[FN + 1] = {0};
+        uint32_t rr[4] = {0, 0, 0, 0};
+        for (int32_t n = 0; n < FN; ++n) {
+            if ((n & 3) == 0) {
+                uint32_t ctr[4] = { (uint32_t)run, (uint32_t)((uint64_t)run >> 32), tag, (epoch << 8) | (uint32_t)(1 + (n >> 2)) };
+                uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+                n2v_oracle_philox4x32_10(ctr, key, rr);
+            }
+            int32_t t = bisect_left_u32(cum_table, V, rr[n & 3] % cum_last) >> lg;
+            if ((((int64_t)t << lg) | part) >= V) --t;
+            tg[n] = t;
+        }
+        for (int32_t d1 = 0; d1 < FN; ++d1)
+            for (int32_t d2 = d1 + 1; d2 < FN; ++d2) if (tg[d1] == tg[d2]) skip_base[d2 + 1] = 1;
+        for (int32_t d = 1; d <= FN; ++d) {
+            if (skip_base[d]) continue;
+            memcpy(out + (size_t)d * dim, syn1_part + (int64_t)tg[d - 1] * dim, sizeof(float) * (size_t)dim);
+            memcpy(orig + (size_t)d * dim, out + (size_t)d * dim, sizeof(float) * (size_t)dim);
+        }
+        int32_t cur_c = -1;
+        const int64_t p0 = run * K, p1 = p0 + K < n_pairs ? p0 + K : n_pairs;
+        for (int64_t q = p0; q <= p1; ++q) {
+            const int32_t c = q < p1 ? pairs[2 * q] : -2;
+            if (c != cur_c) {
+                if (cur_c >= 0) {
+                    float *row = syn1_part + (int64_t)cur_c * dim;
+                    for (int32_t i = 0; i < dim; ++i) row[i] += out[i] - orig[i];
+                }
+                if (q == p1) break;
+                memcpy(out, syn1_part + (int64_t)c * dim, sizeof(float) * (size_t)dim);
+                memcpy(orig, out, sizeof(float) * (size_t)dim);
+                cur_c = c;
+            }
+            float *row1 = syn0_part + (int64_t)pairs[2 * q + 1] * dim;
+            float g[FN + 1];
+            for (int32_t d = 0; d <= FN; ++d) {
+                g[d] = 0.0f;
+                if (d > 0 && (skip_base[d] || tg[d - 1] == c)) continue;
+                const float *row2 = out + (size_t)d * dim;
+                float f = 0.0f;
+                for (int32_t i = 0; i < dim; ++i) f += row1[i] * row2[i];
+                if (f <= -MAX_EXP || f >= MAX_EXP) continue;
+                f = EXP_TABLE[(int)((f + MAX_EXP) * (EXP_TABLE_SIZE / MAX_EXP / 2))];
+                g[d] = ((d == 0 ? 1.0f : 0.0f) - f) * alpha;
+            }
+            memset(work, 0, sizeof(float) * (size_t)dim);
+            for (int32_t d = 0; d <= FN; ++d) {
+                float *row2 = out + (size_t)d * dim;
+                if (d > 0 && skip_base[d]) continue;
+                for (int32_t i = 0; i < dim; ++i) work[i] += g[d] * row2[i];
+                for (int32_t i = 0; i < dim; ++i) row2[i] += g[d] * row1[i];
+            }
+            for (int32_t i = 0; i < dim; ++i) row1[i] += work[i];
+        }
+        for (int32_t d = 1; d <= FN; ++d) {
+            if (skip_base[d]) continue;
+            float *row = syn1_part + (int64_t)tg[d - 1] * dim;
+            for (int32_t i = 0; i < dim; ++i) row[i] += out[(size_t)d * dim + i] - orig[(size_t)d * dim + i];
+        }
+    }
+    free(out);
+    return 0;
+}
