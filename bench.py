@@ -11,9 +11,12 @@ edges after symmetrise/dedup, rejection-sampling walker, p=0.25 q=4, R=10 walks 
 SGNS d=128 window=10 negative=5 sample=1e-3 (the main.py defaults). A STEP is one pass of the hot
 path over one batch: `batch_walks` walks per GPU are simulated (n2v_walk_reject) and the batch is
 trained on (n2v_sgns_train); with N > 1 the walk ids of a step are split across ranks (weak
-scaling: batch per GPU fixed) and the replicated tables are combined by a delta-sum NCCL
-all-reduce every `sync_walks` walks per rank (default: the largest interval that keeps
-link-prediction AUC within +-0.005 of one replica, node2vec_by_ecc_b200.dist).
+scaling: batch per GPU fixed) and SGNS runs block-partitioned (--multi-gpu-sgns block, the
+default): the tables are cut into N row sets, the step's walks of all GPUs form one pool, GPU k
+trains the pair bucket (centre in part k, context in part (k + e) % N) in sub-step e and the syn0
+parts travel round an NCCL ring -- no replicas (node2vec_by_ecc_b200.word2vec.BlockSgnsTrainer).
+`replica` (full copies, delta-sum all-reduce every `sync_walks` walks) and `peer` (one table pair
+in NVLink peer memory) are the measured alternatives.
 value = (centre, context) pairs trained per second through the whole step, all ranks.
 Inputs are larger than L2 (tables 2 x 1.35 GB, CSR 0.8 GB, arc hash 4.3 GB), no L2 flush needed.
 """
@@ -67,9 +70,12 @@ def parse():
     ap.add_argument("--sync-walks", type=int, default=0,
                     help="walks per rank between two delta-sum syncs of the replicated tables (N > 1); "
                          "0 = auto (total pairs per sync <= 100 V / N), -1 = once per step")
-    ap.add_argument("--multi-gpu-sgns", default="replica", choices=["peer", "replica"],
-                    help="N > 1: peer = one table pair sharded over the GPUs' HBM, trained over NVLink peer "
-                         "memory; replica = a full copy per GPU, delta-sum all-reduce every --sync-walks")
+    ap.add_argument("--multi-gpu-sgns", default="block", choices=["block", "peer", "replica"],
+                    help="N > 1: block = tables cut into N row sets, orthogonal (centre part, context part) pair "
+                         "buckets per sub-step, syn0 parts passed round a ring (no replicas); peer = one table pair "
+                         "sharded over the GPUs' HBM, trained over NVLink peer memory; replica = a full copy per GPU, "
+                         "delta-sum all-reduce every --sync-walks")
+    ap.add_argument("--run-pairs", type=int, default=32, help="block mode: pairs sharing one negative set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -196,7 +202,12 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(counts)
     peer = world > 1 and a.multi_gpu_sgns == "peer" and bool(a.shared_negatives)
-    if peer:      # ONE table pair spread over the GPUs' HBM, trained by all of them over NVLink
+    block = world > 1 and a.multi_gpu_sgns == "block" and bool(a.shared_negatives)
+    if block:     # tables cut into `world` row sets; orthogonal pair buckets; syn0 parts round a ring
+        from node2vec_by_ecc_b200 import BlockSgnsTrainer
+        trainer = BlockSgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1,
+                                   run_pairs=a.run_pairs)
+    elif peer:    # ONE table pair spread over the GPUs' HBM, trained by all of them over NVLink
         from node2vec_by_ecc_b200 import PeerSgnsTrainer
         trainer = PeerSgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
     else:
@@ -211,9 +222,9 @@ def run_ours(a):
 
     mode = {"shared": int(a.shared_negatives)}
     from node2vec_by_ecc_b200.dist import ReplicaSync, sync_walks_per_rank
-    replica_sync = None if peer else ReplicaSync(trainer.syn0, trainer.syn1neg)
+    replica_sync = None if (peer or block) else ReplicaSync(trainer.syn0, trainer.syn1neg)
     pairs_per_walk = (2 * a.window + 1) * L / 2.0            # ~ mean reduced window = (window + 1) / 2 each side
-    if world == 1 or peer or a.sync_walks < 0:
+    if world == 1 or peer or block or a.sync_walks < 0:
         sync_walks = B
     elif a.sync_walks > 0:
         sync_walks = min(B, a.sync_walks)
@@ -238,10 +249,14 @@ def run_ours(a):
             sb_ = min(B, sa + sync_walks)
             e2, e3 = ev(), ev()
             e2.record()
-            trainer.train(walks[sa:sb_], None, sb_ - sa, L, total_examples=total_walks,
-                          example_base=(g0 + sa) % total_walks, sent_id_base=g0 + sa, sent_per_job=10000 // L,
-                          grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
-                          atomic_updates=a.atomic, negative_sharing=mode["shared"])
+            if block:     # one pool = this step's walks of all ranks (rank order = global walk id order)
+                trainer.train(walks, None, B, L, total_examples=total_walks, example_base=(i * world * B) % total_walks,
+                              sent_id_base=i * world * B, grid_warps=a.hogwild_warps or None)
+            else:
+                trainer.train(walks[sa:sb_], None, sb_ - sa, L, total_examples=total_walks,
+                              example_base=(g0 + sa) % total_walks, sent_id_base=g0 + sa, sent_per_job=10000 // L,
+                              grid_warps=a.hogwild_warps or trainer.default_hogwild_warps(bool(mode["shared"])),
+                              atomic_updates=a.atomic, negative_sharing=mode["shared"])
             e3.record()
             if replica_sync is not None:
                 replica_sync.sync()
@@ -279,8 +294,16 @@ def run_ours(a):
     for i in range(a.warmup):
         step(i)
     sampler = ClockSampler(local) if rank == 0 else None
+    if block:
+        trainer.phase_events = []
     ms, pairs, cn, centres = timed(a.warmup, record=True)
     clocks = sampler.stop() if sampler else None
+    phases = None
+    if block:     # rank 0's split of the SGNS phase: pool all-gather, pair expansion, bucket kernels, ring passes
+        phases = {}
+        for name, x, y in trainer.phase_events:
+            phases[name] = phases.get(name, 0.0) + x.elapsed_time(y)
+        trainer.phase_events = None
     walk_ms = sum(x.elapsed_time(y) for x, y in kern["walk"])
     sgns_ms = sum(x.elapsed_time(y) for x, y in kern["sgns"])
     my_pairs_rank = pairs / world
@@ -302,7 +325,7 @@ def run_ours(a):
                "api": "DeviceGraph.walk_reject -> host -> SgnsTrainer.train (pinned host buffers)"}
 
     other = None
-    if not a.no_e2e and not peer:      # the other negative-sampling mode, same steps, kernel-timed
+    if not a.no_e2e and not peer and not block:      # the other negative-sampling mode, same steps, kernel-timed
         kern_main = kern
         kern = {"walk": [], "sgns": []}
         mode["shared"] = 1 - mode["shared"]
@@ -318,7 +341,14 @@ def run_ours(a):
     out = None
     if rank == 0:
         peak, src = peaks()
-        if a.shared_negatives:
+        k_ms = sgns_ms
+        if block:
+            # block kernel: per pair the input row, per carried output row (centre changes + the 5
+            # negatives of a run) one read + one reduction: 1,024 B each; `centres` = carried rows
+            alg_bytes = (my_pairs_rank + centres / world) * 1024.0
+            kname = "sgns_block_kernel (one negative set per run of %d pairs)" % a.run_pairs
+            k_ms = phases["train"]
+        elif a.shared_negatives:
             # shared-negative kernel: per pair the input row (read + written, 1,024 B), per centre
             # the 6 carried output rows (read + written once, 6,144 B)
             alg_bytes = (my_pairs_rank * 1024.0 + centres / world * 6144.0)
@@ -326,14 +356,16 @@ def run_ours(a):
         else:
             alg_bytes = my_pairs_rank * float(BYTES_PER_PAIR)
             kname = "sgns_train_kernel_v2 (per-pair negatives)"
-        sg_gbs = alg_bytes / (sgns_ms / 1e3) / 1e9
+        n_launch = max(1, len(kern["sgns"])) * (world if block else 1)
+        sg_gbs = alg_bytes / (k_ms / 1e3) / 1e9
         roof = {"kernel": kname, "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
                 "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]) if (a.scale == 22 and a.batch_walks == 1 << 19 and world == 1) else None,
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)", "peak_source": src,
-                "algorithmic_bytes_per_launch": alg_bytes / max(1, len(kern["sgns"])),
-                "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / max(1, len(kern["sgns"])),
-                "centres_per_launch": centres / world / max(1, len(kern["sgns"])), "ms_per_launch": sgns_ms / max(1, len(kern["sgns"])),
-                "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (sgns_ms / 1e3) / 1e9}
+                "algorithmic_bytes_per_launch": alg_bytes / n_launch,
+                "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / n_launch,
+                ("carried_rows_per_launch" if block else "centres_per_launch"): centres / world / n_launch,
+                "ms_per_launch": k_ms / n_launch,
+                "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (k_ms / 1e3) / 1e9}
         if tables is None:
             S, T, P = (float(cn[0]) / world, float(cn[1]) / world, float(cn[3]) / world)
             wbytes = 20 * S + 4 * T + 4 * P
@@ -356,8 +388,14 @@ def run_ours(a):
             "walk_steps_per_s": (float(cn[0]) if tables is None else S * world) / (walk_ms / 1e3),
             "sgns_pairs_per_s_kernel": pairs / (sgns_ms / 1e3),
             "roofline": roof, "roofline_walk": roof_walk, "e2e": e2e, "other_negative_mode": other,
-            "gpu_launches": a.steps * (1 + (B + sync_walks - 1) // sync_walks),
+            "gpu_launches": a.steps * ((1 + 2 + world) if block else (1 + (B + sync_walks - 1) // sync_walks)),
+            "sgns_phases_ms_per_step": ({k: v / a.steps for k, v in phases.items()} if phases else None),
             "multi_gpu_sgns": None if world == 1 else (
+                {"tables": "cut into N row sets (row i -> GPU i % N); a step's walks of all GPUs form one pool (all-gather, "
+                           "4 B/token); GPU k expands the pairs whose centre is in part k, bucketed by the context's part, and "
+                           "trains bucket (k, (k + e) % N) in sub-step e against syn1neg part k and the syn0 part it holds, "
+                           "which then moves to GPU k - 1 (NCCL send/recv ring); no replicas, no averaging",
+                 "run_pairs": a.run_pairs, "pool_walks": B * world} if block else
                 {"tables": "one syn0/syn1neg pair, row i in GPU i % N's HBM, every GPU trains its own walks against all parts "
                            "over NVLink peer memory (red.global.add.v4.f32); no replicas, no sync"} if peer else
                 {"tables": "replicated; delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,

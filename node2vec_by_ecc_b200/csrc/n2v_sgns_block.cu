@@ -18,7 +18,8 @@
 // count^0.75 table and mapped to the same-rank word of part k), carried in registers for the run
 // together with the current centre row; a row repeated inside the set is used once, a negative
 // equal to the pair's centre is skipped for that pair (gensim's rule). Per pair only syn0[context]
-// moves: 1,024 B + 1,024 B per centre change + 5,120 B / run_pairs.
+// moves: 1,024 B per pair + 1,024 B per carried row (centre changes + 5 per run; counted in
+// pairs_out[1]).
 #include <cub/cub.cuh>
 
 #include "n2v_common.cuh"
@@ -70,9 +71,13 @@ sgns_pairs_kernel(PairsArgs g)
         int32_t n_kept = 0, c_lo = 0, c_hi = 0;
         bool first_chunk = true;
         while (next_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept, c_lo, c_hi, first_chunk)) {
-            for (int32_t i = c_lo; i < c_hi; ++i) {
+            // the centres of this part, in order: 32 candidates per ballot, then only the set bits
+            for (int32_t i0 = c_lo; i0 < c_hi; i0 += 32) {
+              uint32_t todo = __ballot_sync(0xFFFFFFFFu, i0 + lane < c_hi && (ws.idx[i0 + lane] & mask) == g.part);
+              while (todo) {
+                const int32_t i = i0 + __ffs(todo) - 1;
+                todo &= todo - 1;
                 const int32_t centre = ws.idx[i];
-                if ((centre & mask) != g.part) continue;
                 int32_t j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
                 int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 for (int32_t jb = j0; jb < kend; jb += 32) {
@@ -93,6 +98,7 @@ sgns_pairs_kernel(PairsArgs g)
                         else if (rank == 0) atomicAdd(g.overflow, 1ull);
                     }
                 }
+              }
             }
             __syncwarp();
         }
@@ -135,7 +141,7 @@ sgns_block_kernel(BlockArgs a)
     const float alpha = a.alpha;
     float *const syn0 = a.syn0_part, *const syn1 = a.syn1neg_part;
     const int64_t n_runs = (a.n_pairs + K - 1) / K;
-    unsigned long long pairs = 0, runs = 0;
+    unsigned long long pairs = 0, carried = 0;      // carried = output rows read into registers
     auto r0 = [&](int32_t l) -> float * { return syn0 + (int64_t)l * dim; };
     auto r1 = [&](int32_t l) -> float * { return syn1 + (int64_t)l * dim; };
     auto sigmoid_g = [&](float f, float label) -> float {
@@ -155,11 +161,15 @@ sgns_block_kernel(BlockArgs a)
         return t;
     };
 
+    uint2 mine_next = (warp * K + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + warp * K + lane) : make_uint2(0u, 0u);
     for (int64_t run = warp; run < n_runs; run += n_warps) {
         const int64_t p0 = run * K;
         const int32_t cnt = (int32_t)((a.n_pairs - p0) < K ? (a.n_pairs - p0) : K);
-        uint2 mine = make_uint2(0u, 0u);
-        if (lane < cnt) mine = __ldcs(a.pairs + p0 + lane);
+        const uint2 mine = mine_next;
+        {                                                        // the next run's pairs: in flight during this run
+            const int64_t pn = (run + n_warps) * K;
+            mine_next = (pn + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + pn + lane) : make_uint2(0u, 0u);
+        }
         const int32_t t_run = draw_run(run);
         int32_t tg[FN];
         uint32_t base_skip = 0xC0u;                            // padding targets 6, 7
@@ -176,7 +186,9 @@ sgns_block_kernel(BlockArgs a)
             out[d + 1] = (on && !((base_skip >> (d + 1)) & 1u)) ? ldcg4(r1(tg[d]), lane) : zero4;
 #pragma unroll
         for (int d = 1; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
-        int32_t cur_c = -1;
+        carried += (unsigned long long)(FN - __popc(base_skip & 0x3Eu));
+        int32_t cur_c = -1, ahead_c = -1;
+        float4 ahead = zero4;                                   // the next centre's row, read one pair early
         uint32_t skipmask = base_skip;
         int32_t ctx = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.y, 0);
         float4 row1 = on ? ldcg4(r0(ctx), lane) : zero4;
@@ -190,16 +202,18 @@ sgns_block_kernel(BlockArgs a)
                     const float4 og = s_orig[wib][0][lane];
                     add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
                 }
-                out[0] = on ? ldcg4(r1(c), lane) : zero4;
+                out[0] = ahead_c == c ? ahead : (on ? ldcg4(r1(c), lane) : zero4);
                 s_orig[wib][0][lane] = out[0];
                 cur_c = c;
+                ++carried;
                 skipmask = base_skip;
 #pragma unroll
                 for (int d = 0; d < FN; ++d) if (tg[d] == c) skipmask |= 2u << d;   // skipped, not redrawn
             }
-            if (c_n != c && on) prefetch_row_l2(r1(c_n), lane);
-            // next input row always in flight; stale only if it is the row this pair updates
+            // the next centre row and the next input row are read one pair early (no write of this warp
+            // can hit the former before use; the latter is stale only if it is the row this pair updates)
             const bool stale = ctx_n == ctx;
+            if (c_n != c) { ahead = on ? ldcg4(r1(c_n), lane) : zero4; ahead_c = c_n; }
             const float4 row1n = on ? ldcg4(r0(ctx_n), lane) : zero4;
 
             // 6 dot products by the transposing butterfly of the sentence-major kernel (n2v_sgns.cu)
@@ -248,10 +262,189 @@ sgns_block_kernel(BlockArgs a)
                             make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w), out[d], on);
         }
         pairs += (unsigned long long)cnt;
-        ++runs;
         __syncwarp();
     }
-    if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, runs); }
+    if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, carried); }
+}
+
+// ---- the same kernel with the look-ahead rows staged through shared memory by cp.async ------------
+// ptxas gives the register look-ahead load of sgns_block_kernel the scoreboard the very next FMUL
+// waits on (scripts/sass_scoreboards.py), so its latency is exposed in full; cp.async has no register
+// destination and no scoreboard: the input row of pair q + 2 and, when the centre changes there, its
+// centre row are copied global -> shared two pairs ahead (one commit group per pair, wait_group 1),
+// every lane moving and later reading only its own 16 bytes (no warp synchronisation needed). A row
+// fetched before one of this warp's own writes to it landed is re-read (input row: same context as
+// one of the two previous pairs; centre row: the centre two pairs back, flushed one pair back).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+template <bool ATOMIC, bool FULL>
+__global__ void __launch_bounds__(SGNS_BLOCK, N2V_BLK_MINB)
+sgns_block_kernel_async(BlockArgs a)
+{
+    constexpr int FN = BLK_FN;
+    constexpr int W = SGNS_BLOCK / 32;
+    __shared__ float s_exp[EXP_TABLE_SIZE];
+    __shared__ float4 s_orig[W][FN][32];           // the run's negative rows as first read
+    __shared__ float4 s_ctx[W][4][32];             // ring: input rows of pairs q .. q + 2
+    __shared__ float4 s_cen[W][4][32];             // ring: centre rows (current one = its first-read copy)
+    for (int i = threadIdx.x; i < EXP_TABLE_SIZE; i += blockDim.x) s_exp[i] = exp_table_entry(i);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = a.grid_warps;
+    if (warp >= n_warps) return;
+    const int32_t dim = FULL ? 128 : a.dim, K = a.run_pairs;
+    const bool on = FULL || (lane * 4 < dim);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const float alpha = a.alpha;
+    float *const syn0 = a.syn0_part, *const syn1 = a.syn1neg_part;
+    const int64_t n_runs = (a.n_pairs + K - 1) / K;
+    unsigned long long pairs = 0, carried = 0;
+    auto r0 = [&](int32_t l) -> float * { return syn0 + (int64_t)l * dim; };
+    auto r1 = [&](int32_t l) -> float * { return syn1 + (int64_t)l * dim; };
+    auto sigmoid_g = [&](float f, float label) -> float {
+        return (label - s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
+    };
+    auto draw_run = [&](int64_t r) -> int32_t {
+        int32_t t = -1;
+        if (lane < FN) {
+            const Philox4 ph = philox4x32_10((uint32_t)r, (uint32_t)((uint64_t)r >> 32), a.tag,
+                                             (a.epoch << 8) | (uint32_t)(1 + (lane >> 2)), k0, k1);
+            const uint32_t rr = (lane & 3) == 0 ? ph.x : (lane & 3) == 1 ? ph.y : (lane & 3) == 2 ? ph.z : ph.w;
+            t = draw_negative(rr, a.cum_table, a.bucket_lo, a.V, a.bucket_bits) >> a.lg;
+            if ((((int64_t)t << a.lg) | a.part) >= a.V) --t;
+        }
+        return t;
+    };
+    for (int d = 0; d < 4; ++d) { s_ctx[wib][d][lane] = zero4; s_cen[wib][d][lane] = zero4; }   // lanes beyond dim read zeros
+
+    uint2 mine_next = (warp * K + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + warp * K + lane) : make_uint2(0u, 0u);
+    for (int64_t run = warp; run < n_runs; run += n_warps) {
+        const int64_t p0 = run * K;
+        const int32_t cnt = (int32_t)((a.n_pairs - p0) < K ? (a.n_pairs - p0) : K);
+        const uint2 mine = mine_next;
+        {
+            const int64_t pn = (run + n_warps) * K;
+            mine_next = (pn + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + pn + lane) : make_uint2(0u, 0u);
+        }
+        // fetch(q): input row of pair q and, if the centre changes at q, its centre row; one group per pair
+        uint32_t cen_issued = 0, cen_used = 0;
+        auto fetch = [&](int32_t q) {
+            if (q < cnt) {
+                const int32_t x = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.y, q);
+                const int32_t c = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.x, q);
+                const int32_t cp = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.x, q > 0 ? q - 1 : 0);
+                if (on) cp_async16(&s_ctx[wib][q & 3][lane], reinterpret_cast<const float4 *>(r0(x)) + lane);
+                if (q == 0 || c != cp) {
+                    if (on) cp_async16(&s_cen[wib][cen_issued & 3][lane], reinterpret_cast<const float4 *>(r1(c)) + lane);
+                    ++cen_issued;
+                }
+            }
+            cp_async_commit();
+        };
+        fetch(0);
+        fetch(1);
+        const int32_t t_run = draw_run(run);
+        int32_t tg[FN];
+        uint32_t base_skip = 0xC0u;
+#pragma unroll
+        for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_run, d);
+#pragma unroll
+        for (int d1 = 0; d1 < FN; ++d1)
+#pragma unroll
+            for (int d2 = d1 + 1; d2 < FN; ++d2) if (tg[d1] == tg[d2]) base_skip |= 2u << d2;
+        float4 out[FN + 1];
+        out[0] = zero4;
+#pragma unroll
+        for (int d = 0; d < FN; ++d)
+            out[d + 1] = (on && !((base_skip >> (d + 1)) & 1u)) ? ldcg4(r1(tg[d]), lane) : zero4;
+#pragma unroll
+        for (int d = 0; d < FN; ++d) s_orig[wib][d][lane] = out[d + 1];
+        carried += (unsigned long long)(FN - __popc(base_skip & 0x3Eu));
+        int32_t cur_c = -1, prev_c = -1;             // prev_c: the centre before cur_c (flushed when cur_c was taken)
+        int32_t ctx_m1 = -1, ctx_m2 = -1;
+        uint32_t skipmask = base_skip;
+        for (int32_t q = 0; q < cnt; ++q) {
+            cp_async_wait1();                          // all groups but pair q + 1's have landed
+            const int32_t c = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.x, q);
+            const int32_t ctx = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.y, q);
+            if (c != cur_c) {                          // centre row: write back, take the next
+                if (cur_c >= 0) {
+                    const float4 og = s_cen[wib][(cen_used - 1) & 3][lane];
+                    add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
+                }
+                float4 *slot = &s_cen[wib][cen_used & 3][lane];
+                if (c == prev_c) { if (on) *slot = ldcg4(r1(c), lane); }   // fetched before its own flush landed
+                out[0] = *slot;
+                ++cen_used;
+                prev_c = cur_c;
+                cur_c = c;
+                ++carried;
+                skipmask = base_skip;
+#pragma unroll
+                for (int d = 0; d < FN; ++d) if (tg[d] == c) skipmask |= 2u << d;
+            }
+            fetch(q + 2);                              // after this pair's centre flush, before its input-row update
+            float4 row1 = s_ctx[wib][q & 3][lane];
+            if (ctx == ctx_m1 || ctx == ctx_m2) row1 = on ? ldcg4(r0(ctx), lane) : zero4;   // fetched before an update of it
+            ctx_m2 = ctx_m1; ctx_m1 = ctx;
+
+            float a0, a1, a2, a3;
+            {
+                const float d0 = dot4(row1, out[0]), d1 = dot4(row1, out[1]), d2 = dot4(row1, out[2]),
+                            d3 = dot4(row1, out[3]), d4 = dot4(row1, out[4]), d5 = dot4(row1, out[5]);
+                const bool h = lane & 16;
+                a0 = (h ? d4 : d0) + __shfl_xor_sync(0xFFFFFFFFu, h ? d0 : d4, 16);
+                a1 = (h ? d5 : d1) + __shfl_xor_sync(0xFFFFFFFFu, h ? d1 : d5, 16);
+                a2 = (h ? 0.f : d2) + __shfl_xor_sync(0xFFFFFFFFu, h ? d2 : 0.f, 16);
+                a3 = (h ? 0.f : d3) + __shfl_xor_sync(0xFFFFFFFFu, h ? d3 : 0.f, 16);
+            }
+            float fv;
+            {
+                const bool h8 = lane & 8, h4 = lane & 4;
+                const float b0 = (h8 ? a2 : a0) + __shfl_xor_sync(0xFFFFFFFFu, h8 ? a0 : a2, 8);
+                const float b1 = (h8 ? a3 : a1) + __shfl_xor_sync(0xFFFFFFFFu, h8 ? a1 : a3, 8);
+                fv = (h4 ? b1 : b0) + __shfl_xor_sync(0xFFFFFFFFu, h4 ? b0 : b1, 4);
+                fv += __shfl_xor_sync(0xFFFFFFFFu, fv, 2);
+                fv += __shfl_xor_sync(0xFFFFFFFFu, fv, 1);
+            }
+            float gv = 0.0f;
+            if (!((skipmask >> (lane >> 2)) & 1u) && fv > -(float)MAX_EXP && fv < (float)MAX_EXP)
+                gv = sigmoid_g(fv, lane < 4 ? 1.0f : 0.0f);
+            float4 work = zero4;
+#pragma unroll
+            for (int d = 0; d <= FN; ++d) {
+                const float gd = __shfl_sync(0xFFFFFFFFu, gv, d * 4);
+                axpy4(work, gd, out[d]);
+                axpy4(out[d], gd, row1);
+            }
+            float4 upd1 = row1;
+            upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
+            add_row<ATOMIC>(r0(ctx), lane, work, upd1, on);
+        }
+        if (cur_c >= 0) {
+            const float4 og = s_cen[wib][(cen_used - 1) & 3][lane];
+            add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
+        }
+#pragma unroll
+        for (int d = 1; d <= FN; ++d) {
+            if ((base_skip >> d) & 1u) continue;
+            const float4 og = s_orig[wib][d - 1][lane];
+            add_row<ATOMIC>(r1(tg[d - 1]), lane,
+                            make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w), out[d], on);
+        }
+        pairs += (unsigned long long)cnt;
+        __syncwarp();
+    }
+    if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, carried); }
 }
 
 static inline size_t blk_align(size_t x, size_t al = 256) { return (x + al - 1) / al * al; }
@@ -375,7 +568,11 @@ extern "C" int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const
     const int wpb = SGNS_BLOCK / 32;
     const int blocks = (a.grid_warps + wpb - 1) / wpb;
     const bool full = params->dim == 128;
-    if (params->atomic_updates) {
+    const bool reg_lookahead = (params->tuning & 1) != 0;     // 1: register look-ahead kernel (kept for comparison)
+    if (params->atomic_updates && !reg_lookahead) {
+        if (full) sgns_block_kernel_async<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        else sgns_block_kernel_async<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+    } else if (params->atomic_updates) {
         if (full) sgns_block_kernel<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         else sgns_block_kernel<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
     } else {

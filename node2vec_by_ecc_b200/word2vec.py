@@ -368,7 +368,7 @@ class BlockSgnsTrainer(SgnsTrainer):
         single-GPU trainer over a pair stream).
     alpha is fixed per pool: alpha0 - (alpha0 - min_alpha) * example_base / total_examples."""
 
-    def __init__(self, counts_by_id, *args, local_parts: int = 0, run_pairs: int = 16, **kw):
+    def __init__(self, counts_by_id, *args, local_parts: int = 0, run_pairs: int = 32, **kw):
         from . import dist as D
         self._rank, self._world = D.world()
         self._local_parts = int(local_parts)
@@ -378,6 +378,7 @@ class BlockSgnsTrainer(SgnsTrainer):
         self.run_pairs = int(run_pairs)
         self._pool = 0
         self._buf = {}
+        self.phase_events = None          # set to [] to record (phase, start event, end event) per train()
         super().__init__(counts_by_id, *args, **kw)
         if self.V < self.n_parts:
             raise ValueError("fewer vocabulary rows than parts")
@@ -415,7 +416,7 @@ class BlockSgnsTrainer(SgnsTrainer):
         P.alpha0, P.min_alpha, P.total_examples, P.example_base, P.sent_per_job = self.alpha, self.min_alpha, 1, 0, 1
         P.epoch, P.seed = int(epoch), self.seed
         P.grid_warps = int(grid_warps or self.default_hogwild_warps())
-        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
+        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, int(os.environ.get("N2V_BLK_TUNING", "0"))
         return P
 
     def make_pairs(self, tokens, sent_off, n_sent, stride, sent_id_base, P, part):
@@ -458,6 +459,8 @@ class BlockSgnsTrainer(SgnsTrainer):
         from . import dist as D
         W = self.n_parts
         multi = not self._local_parts and W > 1
+        mark = self._mark
+        t = mark()
         if multi:
             if sent_off is not None:
                 raise NotImplementedError("multi-GPU pools are fixed-stride walk buffers")
@@ -465,9 +468,11 @@ class BlockSgnsTrainer(SgnsTrainer):
             n_sent = n_sent * W
         if n_sent <= 0:
             return
+        t = mark("gather", t)
         P = self._params(epoch, grid_warps)
         al = self.pool_alpha(example_base, total_examples, alpha, min_alpha)
         streams = {k: self.make_pairs(tokens, sent_off, n_sent, stride, sent_id_base, P, k) for k in self._mine}
+        t = mark("pairs", t)
         held = None if self._local_parts else self.parts0[self._rank]
         for e in range(W):
             for k in self._mine:
@@ -475,11 +480,22 @@ class BlockSgnsTrainer(SgnsTrainer):
                 pairs, bounds = streams[k]
                 self.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b],
                                   self.parts0[b] if self._local_parts else held, k, b, P, al)
+            t = mark("train", t)
             if multi:                                    # the syn0 part moves on; after W passes it is home again
                 held, self._spare = D.ring_pass(held, self._spare)
+                t = mark("ring", t)
         if multi:
             self.parts0[self._rank] = held
         self._pool += 1
+
+    def _mark(self, phase=None, since=None):
+        if self.phase_events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if phase is not None:
+            self.phase_events.append((phase, since, e))
+        return e
 
     def check_overflow(self):
         for b in self._buf.values():

@@ -182,3 +182,70 @@ def test_bench_reference_arm_contract_small():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "pairs/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def _gloo_block_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from node2vec_by_ecc_b200.dist import bucket_of, gather_pool, ring_pass
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    pool = gather_pool(torch.full((3, 4), rank, dtype=torch.int32))
+    ok = pool.shape == (3 * world, 4) and all(int(pool[3 * r + i, 0]) == r for r in range(world) for i in range(3))
+    held, spare = torch.full((5, 2), float(rank)), torch.empty((5, 2))
+    seen = []
+    for e in range(world):                       # sub-step e: this rank must hold part (rank + e) % world
+        seen.append(int(held[0, 0]))
+        ok = ok and int(held[0, 0]) == bucket_of(rank, e, world)
+        held, spare = ring_pass(held, spare)
+    ok = ok and int(held[0, 0]) == rank          # home again after `world` passes
+    q.put((rank, ok, seen))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_block_schedule_ring(world):
+    """BlockSgnsTrainer's host plumbing: pool gathered in rank order; in every sub-step the ranks
+    hold pairwise different syn0 parts (orthogonal buckets) and every rank sees every part once."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gloo_block_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, seen in res:
+        assert ok and sorted(seen) == list(range(world))
+    for e in range(world):
+        assert sorted(r[2][e] for r in res) == list(range(world))
+
+
+def test_oracle_block_streams_cover_sentence_major_pairs():
+    """oracle self-consistency: the pair streams of all (centre part, context part) buckets together
+    are exactly the pairs of the sentence-major law under the same Philox addressing."""
+    import oracle
+    z = np.load(os.path.join(ROOT, "tests", "golden", "karate_p025_q4.npz"))
+    w = z["walks"]
+    voc = oracle.sgns_vocab(w, 34)
+    tok = np.where(w >= 0, voc.id2index[np.maximum(w, 0)], -1).astype(np.int32).ravel()
+    off = np.arange(w.shape[0] + 1, dtype=np.int64) * w.shape[1]
+    _, _, pairs = oracle.sgns_train(tok, off, voc, dim=8, window=10, negative=5, iters=1, workers=1, rng_mode=3, seed=4)
+    whole = oracle.sgns_make_pairs(tok, off, voc, 0, 1, window=10, seed=4)[0]
+    assert len(whole) == pairs
+    for n_parts in (2, 4, 8):
+        got = []
+        for k in range(n_parts):
+            for b, st in enumerate(oracle.sgns_make_pairs(tok, off, voc, k, n_parts, window=10, seed=4)):
+                got.append(np.stack([st[:, 0] * n_parts + k, st[:, 1] * n_parts + b], 1))
+        got = np.concatenate(got)
+        assert len(got) == pairs
+        key = lambda a: np.sort(a[:, 0].astype(np.int64) * 100000 + a[:, 1])
+        assert np.array_equal(key(got), key(whole))
+    # one part: the block law trains every pair once; tables move and stay finite
+    V, dim = voc.V, 16
+    p0 = [oracle.sgns_init_syn0(V, dim, 4)]; p1 = [np.zeros((V, dim), np.float32)]
+    n = oracle.sgns_block_pool(tok, off, voc, p0, p1, window=10, alpha=0.025, run_pairs=16, seed=4)
+    assert n == pairs and np.isfinite(p0[0]).all() and np.abs(p1[0]).max() > 1e-3

@@ -133,3 +133,17 @@ def test_block_wide_close_to_sequential():
     a, b = res[0][1], res[1][1]
     cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
     assert float(cos.mean()) > 0.9
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_ranks_equal_one_device():
+    """torchrun x 2 (NCCL all-gather + ring): bit-identical to all parts on one device"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "scripts", "dist_block_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["max_abs_diff_vs_one_device"] == [0.0, 0.0] and d["moved"] > 1e-3
+    assert d["auc_mean"] > 0.78
