@@ -139,7 +139,9 @@ def config_of(a, n_nodes=None, nnz=None):
                      f"p={a.p} q={a.q}, R={a.num_walks} L={a.walk_length}; SGNS d={a.dim} window={a.window} "
                      f"negative={a.negative} sample=1e-3",
          "batch_walks_per_gpu": a.batch_walks, "generator": "node2vec_by_ecc_b200.synth.rmat_edges seed=1",
-         "sgns_negatives": ("one set of 5 per centre, shared by its context pairs (other_negative_mode = fresh set per pair)"
+         "sgns_negatives": ("one set of 5 per run of %d consecutive pairs of a (centre part, context part) bucket" % a.run_pairs
+                            if (a.shared_negatives and a.gpus > 1 and a.multi_gpu_sgns == "block") else
+                            "one set of 5 per centre, shared by its context pairs (other_negative_mode = fresh set per pair)"
                             if a.shared_negatives else "fresh set of 5 per (centre, context) pair, gensim's law"),
          "l2": "inputs larger than L2 (no flush)"}
     if n_nodes is not None:
@@ -293,11 +295,11 @@ def run_ours(a):
 
     for i in range(a.warmup):
         step(i)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)          # every rank watches its own GPU; rank 0 reports all of them
     if block:
         trainer.phase_events = []
     ms, pairs, cn, centres = timed(a.warmup, record=True)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
     phases = None
     if block:     # rank 0's split of the SGNS phase: pool all-gather, pair expansion, bucket kernels, ring passes
         phases = {}
@@ -306,6 +308,14 @@ def run_ours(a):
         trainer.phase_events = None
     walk_ms = sum(x.elapsed_time(y) for x, y in kern["walk"])
     sgns_ms = sum(x.elapsed_time(y) for x, y in kern["sgns"])
+    by_rank = None
+    if world > 1:      # outside the timed region: every rank's clocks and SGNS phase split, for imbalance / throttling
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, {"rank": rank, "clocks": clocks, "walk_ms_per_step": walk_ms / a.steps,
+                                         "sgns_ms_per_step": sgns_ms / a.steps,
+                                         "sgns_phases_ms_per_step": ({k: v / a.steps for k, v in phases.items()} if phases else None)})
+        bad = sorted({r for x in by_rank for r in x["clocks"]["reasons"]})
+        clocks = dict(clocks, reasons=bad, sm_mhz_min_over_ranks=min((x["clocks"]["sm_mhz"] or 0) for x in by_rank))
     my_pairs_rank = pairs / world
     steps_walked = int(cn[0]) if tables is None else None
 
@@ -322,7 +332,7 @@ def run_ours(a):
         e2e = {"value": pairs_e / (ms_e / 1e3), "unit": "pairs/s",
                "h2d_bytes_per_step": (B * 4 + B * L * 4) * world, "d2h_bytes_per_step": (B * L * 4 + B * 4 + 8) * world,
                "ms_per_step": ms_e / a.steps,
-               "api": "DeviceGraph.walk_reject -> host -> SgnsTrainer.train (pinned host buffers)"}
+               "api": "DeviceGraph.walk_reject -> host -> %s.train (pinned host buffers)" % type(trainer).__name__}
 
     other = None
     if not a.no_e2e and not peer and not block:      # the other negative-sampling mode, same steps, kernel-timed
@@ -400,7 +410,7 @@ def run_ours(a):
                            "over NVLink peer memory (red.global.add.v4.f32); no replicas, no sync"} if peer else
                 {"tables": "replicated; delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,
                  "syncs_per_step": (B + sync_walks - 1) // sync_walks}),
-            "clocks": clocks, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
+            "clocks": clocks, "by_rank": by_rank, "hogwild_warps": grid_warps, "atomic_updates": a.atomic, "shared_negatives": a.shared_negatives, "setup_s": t_setup,
         }
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(a, dg, trainer, walks)
