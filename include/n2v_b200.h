@@ -234,7 +234,9 @@ int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64
  *       consecutive pairs, Philox ctr (run, tag, epoch), each draw mapped to the word of the same
  *       local row in `part`; a row repeated in the set is used once, a negative equal to a pair's
  *       centre is skipped for that pair. alpha is the caller's (one value per call). Uses params->
- *       V, dim (<= 128), negative (5), bucket_bits, seed, epoch, grid_warps, atomic_updates.
+ *       V, dim (<= 128), negative (5), bucket_bits, seed, epoch, grid_warps, atomic_updates, tuning
+ *       (experiment switches, 0 = default: bit 0 register look-ahead kernel, bit 1 per-warp sums for
+ *       the hottest input rows).
  *       pairs_out[0] += pairs, [1] += output rows carried in registers (centre changes + the
  *       negatives of every run): algorithmic bytes = 1,024 * (pairs + carried rows) at dim 128. */
 size_t n2v_sgns_pairs_workspace_bytes(int64_t n_sent, int32_t n_parts);

@@ -283,12 +283,21 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-template <bool ATOMIC, bool FULL>
+// HOTP (experiment, `tuning & 2`, off by default): the few most frequent input rows (local rows
+// [0, HOT): the vocabulary is count-sorted) get their updates summed in a per-warp shared-memory slot
+// and written back every HOT_FLUSH runs instead of one reduction per pair; the warp reads such a row
+// fresh from memory and adds its own pending sum, so a one-warp run still equals the sequential law.
+// Built to test whether the reductions on the hottest row are what makes the buckets of context part
+// 0 slow (25 vs 17 ms, the critical path of the 8-GPU ring): they are not -- the buckets stay slow
+// (the reads of that row are the hot spot) and C2's AUC moves by up to +0.02 (profiles/r01_v_*).
+template <bool ATOMIC, bool FULL, bool HOTP>
 __global__ void __launch_bounds__(SGNS_BLOCK, N2V_BLK_MINB)
 sgns_block_kernel_async(BlockArgs a)
 {
     constexpr int FN = BLK_FN;
     constexpr int W = SGNS_BLOCK / 32;
+    constexpr int HOT = 4, HOT_FLUSH = 8;
+    __shared__ float4 s_hot[HOTP ? W : 1][HOT][32];
     __shared__ float s_exp[EXP_TABLE_SIZE];
     __shared__ float4 s_orig[W][FN][32];           // the run's negative rows as first read
     __shared__ float4 s_ctx[W][4][32];             // ring: input rows of pairs q .. q + 2
@@ -325,6 +334,18 @@ sgns_block_kernel_async(BlockArgs a)
         return t;
     };
     for (int d = 0; d < 4; ++d) { s_ctx[wib][d][lane] = zero4; s_cen[wib][d][lane] = zero4; }   // lanes beyond dim read zeros
+    uint32_t hot_mask = 0;
+    int32_t hot_runs = 0;
+    if (HOTP) for (int h = 0; h < HOT; ++h) s_hot[wib][h][lane] = zero4;
+    auto flush_hot = [&]() {
+        for (int h = 0; h < HOT; ++h)
+            if ((hot_mask >> h) & 1u) {
+                const float4 sum = s_hot[wib][h][lane];
+                add_row<ATOMIC>(r0(h), lane, sum, sum, on);
+                s_hot[wib][h][lane] = zero4;
+            }
+        hot_mask = 0;
+    };
 
     uint2 mine_next = (warp * K + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + warp * K + lane) : make_uint2(0u, 0u);
     for (int64_t run = warp; run < n_runs; run += n_warps) {
@@ -394,7 +415,12 @@ sgns_block_kernel_async(BlockArgs a)
             }
             fetch(q + 2);                              // after this pair's centre flush, before its input-row update
             float4 row1 = s_ctx[wib][q & 3][lane];
-            if (ctx == ctx_m1 || ctx == ctx_m2) row1 = on ? ldcg4(r0(ctx), lane) : zero4;   // fetched before an update of it
+            const bool hot = HOTP && ctx < HOT;
+            if (hot || ctx == ctx_m1 || ctx == ctx_m2) row1 = on ? ldcg4(r0(ctx), lane) : zero4;   // fetched before an update of it
+            if (hot) {                                  // + what this warp still holds back for that row
+                const float4 pend = s_hot[wib][ctx][lane];
+                row1.x += pend.x; row1.y += pend.y; row1.z += pend.z; row1.w += pend.w;
+            }
             ctx_m2 = ctx_m1; ctx_m1 = ctx;
 
             float a0, a1, a2, a3;
@@ -426,10 +452,18 @@ sgns_block_kernel_async(BlockArgs a)
                 axpy4(work, gd, out[d]);
                 axpy4(out[d], gd, row1);
             }
-            float4 upd1 = row1;
-            upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
-            add_row<ATOMIC>(r0(ctx), lane, work, upd1, on);
+            if (hot) {
+                float4 pend = s_hot[wib][ctx][lane];
+                pend.x += work.x; pend.y += work.y; pend.z += work.z; pend.w += work.w;
+                s_hot[wib][ctx][lane] = pend;
+                hot_mask |= 1u << ctx;
+            } else {
+                float4 upd1 = row1;
+                upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
+                add_row<ATOMIC>(r0(ctx), lane, work, upd1, on);
+            }
         }
+        if (HOTP && ++hot_runs >= HOT_FLUSH) { flush_hot(); hot_runs = 0; }
         if (cur_c >= 0) {
             const float4 og = s_cen[wib][(cen_used - 1) & 3][lane];
             add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
@@ -444,6 +478,7 @@ sgns_block_kernel_async(BlockArgs a)
         pairs += (unsigned long long)cnt;
         __syncwarp();
     }
+    if (HOTP) flush_hot();
     if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, carried); }
 }
 
@@ -569,9 +604,12 @@ extern "C" int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const
     const int blocks = (a.grid_warps + wpb - 1) / wpb;
     const bool full = params->dim == 128;
     const bool reg_lookahead = (params->tuning & 1) != 0;     // 1: register look-ahead kernel (kept for comparison)
+    const bool hot_private = (params->tuning & 2) != 0;       // 2: per-warp sums for the hottest input rows
     if (params->atomic_updates && !reg_lookahead) {
-        if (full) sgns_block_kernel_async<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
-        else sgns_block_kernel_async<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        if (full && hot_private) sgns_block_kernel_async<true, true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        else if (full) sgns_block_kernel_async<true, true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        else if (hot_private) sgns_block_kernel_async<true, false, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
+        else sgns_block_kernel_async<true, false, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
     } else if (params->atomic_updates) {
         if (full) sgns_block_kernel<true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         else sgns_block_kernel<true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);

@@ -47,9 +47,17 @@ for parts in [int(x) for x in os.environ.get("PARTS", "1,8").split(",")]:
                     a0.record()
                     pairs, bounds = trn.make_pairs(walks, None, POOL, L, it * POOL, P, k)
                     a1.record()
+                    bev = []
                     for b in range(parts):
+                        x0, x1 = ev(), ev()
+                        x0.record()
                         trn.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b], trn.parts0[b], k, b, P, 0.02)
+                        x1.record()
+                        bev.append((x0, x1, bounds[b + 1] - bounds[b]))
                     a2.record(); torch.cuda.synchronize()
+                    if it == 2 and os.environ.get("BUCKET_TIMES"):     # ms and pairs of every bucket (k, b) of the timed pool
+                        print(json.dumps({"centre_part": k, "bucket_ms": [round(x.elapsed_time(y), 3) for x, y, _ in bev],
+                                          "bucket_pairs": [int(n_) for _, _, n_ in bev]}), flush=True)
                     t_pairs += a0.elapsed_time(a1); t_train += a1.elapsed_time(a2)
             else:
                 e1.record()
