@@ -289,7 +289,8 @@ __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_g
 // fresh from memory and adds its own pending sum, so a one-warp run still equals the sequential law.
 // Built to test whether the reductions on the hottest row are what makes the buckets of context part
 // 0 slow (25 vs 17 ms, the critical path of the 8-GPU ring): they are not -- the buckets stay slow
-// (the reads of that row are the hot spot) and C2's AUC moves by up to +0.02 (profiles/r01_v_*).
+// (so the reads / re-reads of that row remain suspect) and C2's AUC moves by up to +0.02
+// (profiles/r01_v_*).
 template <bool ATOMIC, bool FULL, bool HOTP>
 __global__ void __launch_bounds__(SGNS_BLOCK, N2V_BLK_MINB)
 sgns_block_kernel_async(BlockArgs a)
