@@ -273,8 +273,9 @@ sgns_block_kernel(BlockArgs a)
 // destination and no scoreboard: the input row of pair q + 2 and, when the centre changes there, its
 // centre row are copied global -> shared two pairs ahead (one commit group per pair, wait_group 1),
 // every lane moving and later reading only its own 16 bytes (no warp synchronisation needed). A row
-// fetched before one of this warp's own writes to it landed is re-read (input row: same context as
-// one of the two previous pairs; centre row: the centre two pairs back, flushed one pair back).
+// fetched before one of this warp's own writes to it landed is replaced: an input row whose context
+// equals that of one of the two previous pairs by the value that pair's update produced (kept in
+// registers), a centre row that was flushed one pair back by a re-read.
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
@@ -393,6 +394,7 @@ sgns_block_kernel_async(BlockArgs a)
         carried += (unsigned long long)(FN - __popc(base_skip & 0x3Eu));
         int32_t cur_c = -1, prev_c = -1;             // prev_c: the centre before cur_c (flushed when cur_c was taken)
         int32_t ctx_m1 = -1, ctx_m2 = -1;
+        float4 upd_m1 = zero4, upd_m2 = zero4;       // the input rows of the two previous pairs after their update
         uint32_t skipmask = base_skip;
         for (int32_t q = 0; q < cnt; ++q) {
             cp_async_wait1();                          // all groups but pair q + 1's have landed
@@ -417,12 +419,13 @@ sgns_block_kernel_async(BlockArgs a)
             fetch(q + 2);                              // after this pair's centre flush, before its input-row update
             float4 row1 = s_ctx[wib][q & 3][lane];
             const bool hot = HOTP && ctx < HOT;
-            if (hot || ctx == ctx_m1 || ctx == ctx_m2) row1 = on ? ldcg4(r0(ctx), lane) : zero4;   // fetched before an update of it
-            if (hot) {                                  // + what this warp still holds back for that row
+            if (hot) {                                  // fresh + what this warp still holds back for that row
+                row1 = on ? ldcg4(r0(ctx), lane) : zero4;
                 const float4 pend = s_hot[wib][ctx][lane];
                 row1.x += pend.x; row1.y += pend.y; row1.z += pend.z; row1.w += pend.w;
-            }
-            ctx_m2 = ctx_m1; ctx_m1 = ctx;
+            } else if (ctx == ctx_m1) row1 = upd_m1;    // staged before this warp's own update of the row: take the
+            else if (ctx == ctx_m2) row1 = upd_m2;      // value that update produced (what a re-read would return,
+            ctx_m2 = ctx_m1; ctx_m1 = ctx;              // without a load queued behind the reductions on a hub row)
 
             float a0, a1, a2, a3;
             {
@@ -453,16 +456,17 @@ sgns_block_kernel_async(BlockArgs a)
                 axpy4(work, gd, out[d]);
                 axpy4(out[d], gd, row1);
             }
+            float4 upd1 = row1;
+            upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
             if (hot) {
                 float4 pend = s_hot[wib][ctx][lane];
                 pend.x += work.x; pend.y += work.y; pend.z += work.z; pend.w += work.w;
                 s_hot[wib][ctx][lane] = pend;
                 hot_mask |= 1u << ctx;
             } else {
-                float4 upd1 = row1;
-                upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
                 add_row<ATOMIC>(r0(ctx), lane, work, upd1, on);
             }
+            upd_m2 = upd_m1; upd_m1 = upd1;
         }
         if (HOTP && ++hot_runs >= HOT_FLUSH) { flush_hot(); hot_runs = 0; }
         if (cur_c >= 0) {
