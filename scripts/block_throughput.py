@@ -31,40 +31,28 @@ for parts in [int(x) for x in os.environ.get("PARTS", "1,8").split(",")]:
     for run in [int(x) for x in os.environ.get("RUNS", "16,32").split(",")]:
         trn = BlockSgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=1, local_parts=parts, run_pairs=run)
         P = trn._params(0, None)
-        tm = {"pairs_ms": 0.0, "train_ms": 0.0}
         for it in range(3):                       # 2 warm-up pools, 1 timed
             st = (torch.arange(POOL, dtype=torch.int64, device=dev) + it * POOL) % n
             dg.walk_reject(0.25, 4.0, st.to(torch.int32), L, 1, it * POOL, out=(walks, lens))
             p0 = int(trn.pairs[0])
-            e0, e1, e2 = ev(), ev(), ev()
-            e0.record()
-            streams = {k: trn.make_pairs(walks, None, POOL, L, it * POOL, P, k) for k in range(parts)} if parts == 1 else None
-            if parts > 1:                         # one centre part at a time (buffers reused) keeps memory at 1/n
-                e1.record()
-                t_pairs = t_train = 0.0
-                for k in range(parts):
-                    a0, a1, a2 = ev(), ev(), ev()
-                    a0.record()
-                    pairs, bounds = trn.make_pairs(walks, None, POOL, L, it * POOL, P, k)
-                    a1.record()
-                    bev = []
-                    for b in range(parts):
-                        x0, x1 = ev(), ev()
-                        x0.record()
-                        trn.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b], trn.parts0[b], k, b, P, 0.02)
-                        x1.record()
-                        bev.append((x0, x1, bounds[b + 1] - bounds[b]))
-                    a2.record(); torch.cuda.synchronize()
-                    if it == 2 and os.environ.get("BUCKET_TIMES"):     # ms and pairs of every bucket (k, b) of the timed pool
-                        print(json.dumps({"centre_part": k, "bucket_ms": [round(x.elapsed_time(y), 3) for x, y, _ in bev],
-                                          "bucket_pairs": [int(n_) for _, _, n_ in bev]}), flush=True)
-                    t_pairs += a0.elapsed_time(a1); t_train += a1.elapsed_time(a2)
-            else:
-                e1.record()
-                pairs, bounds = streams[0]
-                trn.train_bucket(pairs, 0, bounds[1], trn.parts0[0], 0, 0, P, 0.02)
-                e2.record(); torch.cuda.synchronize()
-                t_pairs, t_train = e0.elapsed_time(e1), e1.elapsed_time(e2)
+            t_pairs = t_train = 0.0
+            for k in range(parts):                # one centre part after the other, as GPU k would
+                a0, a1, a2 = ev(), ev(), ev()
+                a0.record()
+                pairs, bounds = trn.make_pairs(walks, None, POOL, L, it * POOL, P, k)
+                a1.record()
+                bev = []
+                for b in range(parts):
+                    x0, x1 = ev(), ev()
+                    x0.record()
+                    trn.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b], trn.parts0[b], k, b, P, 0.02)
+                    x1.record()
+                    bev.append((x0, x1, bounds[b + 1] - bounds[b]))
+                a2.record(); torch.cuda.synchronize()
+                t_pairs += a0.elapsed_time(a1); t_train += a1.elapsed_time(a2)
+                if it == 2 and os.environ.get("BUCKET_TIMES"):     # ms and pairs of every bucket (k, b) of the timed pool
+                    print(json.dumps({"centre_part": k, "bucket_ms": [round(x.elapsed_time(y), 3) for x, y, _ in bev],
+                                      "bucket_pairs": [int(n_) for _, _, n_ in bev]}), flush=True)
             npairs = int(trn.pairs[0]) - p0
         trn.check_overflow()
         r = {"parts": parts, "run_pairs": run, "pool_walks": POOL, "pairs": npairs, "make_pairs_ms": t_pairs, "train_ms": t_train,
