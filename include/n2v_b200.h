@@ -124,6 +124,24 @@ int n2v_walk_reject(const int64_t *row_ptr, const int32_t *col, const double *w,
                     uint64_t walk_id_base, int32_t *walks, int32_t *lens,
                     unsigned long long *counters, void *stream);
 
+/* The same walkers with the reference's popularity laws (popwalk = "pop", node2vec.py:154-174,:206-237;
+ * reached from main_link.py:206-219,:274-281). law == NULL: as above.
+ *  first_slots: alias table of the FIRST step (prev absent), e.g. the popularity node tables of
+ *      preprocess_transition_probs_popularity (:213-218: w / len(G[nbr]) for non-item nodes); later steps
+ *      keep the plain get_alias_edge law with node_slots (weighted graphs) / a uniform candidate.
+ *  pop_edges = 1: later steps follow get_alias_edge_pop (:154-174) -- the candidate is drawn from
+ *      node_slots, which the caller builds over w / len(G[nbr]) for EVERY node, and accepted with
+ *      alpha = 1/p on the return edge, 1 elsewhere (the reference does not use q there). */
+typedef struct {
+    const n2v_slot_t *first_slots;
+    int32_t pop_edges;
+} n2v_walk_law_t;
+int n2v_walk_reject_law(const int64_t *row_ptr, const int32_t *col, const double *w,
+                        const n2v_slot_t *node_slots, const n2v_walk_law_t *law, double p, double q,
+                        int symmetric, const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
+                        uint64_t walk_id_base, int32_t *walks, int32_t *lens,
+                        unsigned long long *counters, void *stream);
+
 /* Second form of the rejection walker: hashed distance-1 test + per-lane state machine (one
  * 8-byte load per lane per iteration; lanes never wait for each other's trials). Needs
  *  - packed_rows[v] = row_ptr[v] << 24 | deg(v)          (n2v_pack_rows; *overflow_flag set when
@@ -145,6 +163,13 @@ int n2v_walk_reject_indexed(const uint64_t *packed_rows, const int32_t *col, int
                             const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
                             uint64_t walk_id_base, int32_t *walks, int32_t *lens,
                             unsigned long long *counters, void *stream);
+
+int n2v_walk_reject_indexed_law(const uint64_t *packed_rows, const int32_t *col, int64_t nnz, const double *w,
+                                const double *strength, const n2v_slot_t *node_slots, const n2v_walk_law_t *law,
+                                const unsigned long long *edge_hash, uint64_t hash_capacity, double p, double q,
+                                int symmetric, const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
+                                uint64_t walk_id_base, int32_t *walks, int32_t *lens,
+                                unsigned long long *counters, void *stream);
 
 /* ---- (4) skip-gram negative sampling -----------------------------------------------------
  * replaces: gensim.models.Word2Vec(sentences, size, window, min_count=0, sg=1, ...) as called

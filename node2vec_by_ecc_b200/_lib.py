@@ -18,7 +18,7 @@ EXPORTS = [
     "n2v_last_error", "n2v_version", "n2v_sm_count", "n2v_csr_workspace_bytes", "n2v_csr_from_coo",
     "n2v_etab_workspace_bytes", "n2v_etab_offsets", "n2v_alias_build_nodes", "n2v_alias_build_edges",
     "n2v_walk_alias", "n2v_arc_record_bytes", "n2v_pack_arcs", "n2v_walk_alias_packed", "n2v_walk_reject", "n2v_pack_rows", "n2v_edge_hash_capacity", "n2v_edge_hash_build",
-    "n2v_walk_reject_indexed", "n2v_vocab_count", "n2v_sgns_prepare_workspace_bytes",
+    "n2v_walk_reject_indexed", "n2v_walk_reject_law", "n2v_walk_reject_indexed_law", "n2v_vocab_count", "n2v_sgns_prepare_workspace_bytes",
     "n2v_sgns_prepare", "n2v_sgns_init", "n2v_sgns_train", "n2v_sgns_init_part", "n2v_sgns_train_sharded",
     "n2v_sgns_pairs_workspace_bytes", "n2v_sgns_pairs_count", "n2v_sgns_pairs_fill", "n2v_sgns_train_block", "n2v_cosine_pairs", "n2v_format_workspace_bytes", "n2v_format_walks_offsets", "n2v_format_walks_write", "n2v_parse_workspace_bytes", "n2v_parse_walks_index", "n2v_parse_walks_fill",
     "n2v_random_gather_bench",
@@ -39,6 +39,11 @@ class SgnsParams(C.Structure):
         ("epoch", C.c_uint32), ("seed", C.c_uint64),
         ("grid_warps", C.c_int32), ("atomic_updates", C.c_int32), ("negative_sharing", C.c_int32), ("tuning", C.c_int32),
     ]
+
+
+class WalkLaw(C.Structure):
+    """n2v_walk_law_t"""
+    _fields_ = [("first_slots", C.c_void_p), ("pop_edges", C.c_int32)]
 
 
 def lib():

@@ -764,7 +764,7 @@ static int sgns_train_impl(const int32_t *tokens, const int64_t *sent_off, int64
     N2V_REQUIRE(tokens && cum_table && bucket_lo && (n_parts > 0 || (syn0 && syn1neg)), "NULL buffer");
     N2V_REQUIRE(sent_off || stride > 0, "need sent_off or a positive stride");
     N2V_REQUIRE(p.V > 0 && p.dim > 0 && p.dim % 4 == 0 && p.dim <= 1024, "dim must be a multiple of 4, <= 1024");
-    N2V_REQUIRE(p.window >= 1 && p.window <= 96, "window out of range (1..96)");
+    N2V_REQUIRE(p.window >= 1 && p.window <= SGNS_MAX_WINDOW, "window out of range (1..96)");
     N2V_REQUIRE(p.negative >= 0 && p.negative <= SGNS_MAX_NEG, "negative out of range");
     N2V_REQUIRE(p.max_sentence_len >= 1 && p.max_sentence_len <= 65535, "max_sentence_len out of range");
     N2V_REQUIRE(p.grid_warps >= 1 && p.total_examples >= 1 && p.sent_per_job >= 1, "bad schedule");

@@ -32,7 +32,8 @@ constexpr int BLK_FN = 5;
 
 struct PairsArgs {
     SgnsArgs a;
-    int32_t part, lg, n_parts;
+    int32_t part, lg, n_parts, neg_group;      // neg_group G > 0: bit 31 of the centre field marks the first pair
+                                               // (in its stream) of each block of G token positions of a walk
     int32_t *counts;            // [n_parts][n_sent]           (count pass)
     const int64_t *offsets;     // [n_parts][n_sent] exclusive (fill pass)
     uint2 *pairs; int64_t capacity;
@@ -49,6 +50,7 @@ sgns_pairs_kernel(PairsArgs g)
     __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
     __shared__ long long s_cur[SGNS_BLOCK / 32][BLK_MAX_PARTS];
+    __shared__ int32_t s_last[SGNS_BLOCK / 32][BLK_MAX_PARTS];
     const SgnsArgs &a = g.a;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
@@ -66,6 +68,7 @@ sgns_pairs_kernel(PairsArgs g)
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
         if (lane < BLK_MAX_PARTS)
             s_cur[wib][lane] = (FILL && lane < g.n_parts) ? (long long)g.offsets[(int64_t)lane * a.n_sent + s] : 0ll;
+        if (lane < BLK_MAX_PARTS) s_last[wib][lane] = -1;
         __syncwarp();
         int64_t t_next = 0;
         int32_t n_kept = 0, c_lo = 0, c_hi = 0;
@@ -78,6 +81,7 @@ sgns_pairs_kernel(PairsArgs g)
                 const int32_t i = i0 + __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int32_t centre = ws.idx[i];
+                const int32_t grp = g.neg_group > 0 ? (int32_t)ws.pos[i] / g.neg_group : -1;
                 int32_t j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
                 int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 for (int32_t jb = j0; jb < kend; jb += 32) {
@@ -87,14 +91,15 @@ sgns_pairs_kernel(PairsArgs g)
                     const int32_t b = valid ? (x & mask) : (BLK_MAX_PARTS + lane);
                     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
                     const int rank = __popc(peers & lt);
-                    long long base = 0;
-                    if (valid) base = s_cur[wib][b];
+                    long long base = 0; int32_t lastg = -1;
+                    if (valid) { base = s_cur[wib][b]; lastg = s_last[wib][b]; }
                     __syncwarp();
-                    if (valid && rank == 0) s_cur[wib][b] = base + __popc(peers);
+                    if (valid && rank == 0) { s_cur[wib][b] = base + __popc(peers); s_last[wib][b] = grp; }
                     __syncwarp();
                     if (FILL && valid) {
                         const long long o = base + rank;
-                        if (o < g.capacity) g.pairs[o] = make_uint2((uint32_t)(centre >> g.lg), (uint32_t)(x >> g.lg));
+                        const uint32_t flag = (g.neg_group > 0 && rank == 0 && lastg != grp) ? 0x80000000u : 0u;
+                        if (o < g.capacity) g.pairs[o] = make_uint2((uint32_t)(centre >> g.lg) | flag, (uint32_t)(x >> g.lg));
                         else if (rank == 0) atomicAdd(g.overflow, 1ull);
                     }
                 }
@@ -112,7 +117,7 @@ struct BlockArgs {
     float *syn0_part, *syn1neg_part;
     const uint32_t *cum_table; const int32_t *bucket_lo;
     int32_t V, dim, bucket_bits, part, lg, run_pairs, grid_warps;
-    float alpha; uint64_t seed; uint32_t epoch, tag;
+    float alpha; uint64_t seed; uint32_t epoch, tag; int32_t cut, blocked;
     unsigned long long *pairs_out;
 };
 
@@ -147,46 +152,69 @@ sgns_block_kernel(BlockArgs a)
     auto sigmoid_g = [&](float f, float label) -> float {
         return (label - s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
     };
-    // lane n (< 5) draws negative n of run r: Philox ctr (r lo, r hi, tag, epoch << 8 | 1 + n / 4);
-    // the drawn word is replaced by the word of the same local row in this part
-    auto draw_run = [&](int64_t r) -> int32_t {
+
+    // lane n (< 5) draws negative n of (run r, centre group `sub` of the run): sub = 0 is the run's own
+    // set; with a.cut every centre change inside the run draws a fresh set (sub = index of the pair at
+    // which the centre changes), so negatives are shared only by pairs of ONE centre (the law of the
+    // sentence-major shared-negative kernel)
+    auto draw_sub = [&](int64_t r, int32_t sub) -> int32_t {
         int32_t t = -1;
         if (lane < FN) {
             const Philox4 ph = philox4x32_10((uint32_t)r, (uint32_t)((uint64_t)r >> 32), a.tag,
-                                             (a.epoch << 8) | (uint32_t)(1 + (lane >> 2)), k0, k1);
+                                             (a.epoch << 8) | ((uint32_t)sub << 2) | (uint32_t)(1 + (lane >> 2)), k0, k1);
             const uint32_t rr = (lane & 3) == 0 ? ph.x : (lane & 3) == 1 ? ph.y : (lane & 3) == 2 ? ph.z : ph.w;
             t = draw_negative(rr, a.cum_table, a.bucket_lo, a.V, a.bucket_bits) >> a.lg;
             if ((((int64_t)t << a.lg) | a.part) >= a.V) --t;
         }
         return t;
     };
-
-    uint2 mine_next = (warp * K + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + warp * K + lane) : make_uint2(0u, 0u);
-    for (int64_t run = warp; run < n_runs; run += n_warps) {
+    // runs of a warp: strided (run = warp, warp + n_warps, ...) or, a.blocked, one contiguous range per warp
+    // (concurrent warps then work on far-apart walks, as the sentence-major kernels do)
+    const int64_t per_warp = (n_runs + n_warps - 1) / n_warps;
+    const int64_t run_lo = a.blocked ? warp * per_warp : warp;
+    const int64_t run_hi = a.blocked ? (run_lo + per_warp < n_runs ? run_lo + per_warp : n_runs) : n_runs;
+    const int64_t run_step = a.blocked ? 1 : n_warps;
+    uint2 mine_next = (run_lo * K + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + run_lo * K + lane) : make_uint2(0u, 0u);
+    for (int64_t run = run_lo; run < run_hi; run += run_step) {
         const int64_t p0 = run * K;
         const int32_t cnt = (int32_t)((a.n_pairs - p0) < K ? (a.n_pairs - p0) : K);
-        const uint2 mine = mine_next;
+        uint2 mine = mine_next;
         {                                                        // the next run's pairs: in flight during this run
-            const int64_t pn = (run + n_warps) * K;
+            const int64_t pn = (run + run_step) * K;
             mine_next = (pn + lane < a.n_pairs && lane < K) ? __ldcs(a.pairs + pn + lane) : make_uint2(0u, 0u);
         }
-        const int32_t t_run = draw_run(run);
+        const uint32_t flags = __ballot_sync(0xFFFFFFFFu, (mine.x >> 31) != 0u);   // pairs that open a negative group
+        mine.x &= 0x7FFFFFFFu;
         int32_t tg[FN];
         uint32_t base_skip = 0xC0u;                            // padding targets 6, 7
-#pragma unroll
-        for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_run, d);
-#pragma unroll
-        for (int d1 = 0; d1 < FN; ++d1)
-#pragma unroll
-            for (int d2 = d1 + 1; d2 < FN; ++d2) if (tg[d1] == tg[d2]) base_skip |= 2u << d2;   // repeated row: once
         float4 out[FN + 1];
         out[0] = zero4;
+        auto flush_negs = [&]() {
 #pragma unroll
-        for (int d = 0; d < FN; ++d)
-            out[d + 1] = (on && !((base_skip >> (d + 1)) & 1u)) ? ldcg4(r1(tg[d]), lane) : zero4;
+            for (int d = 1; d <= FN; ++d) {
+                if ((base_skip >> d) & 1u) continue;
+                const float4 og = s_orig[wib][d][lane];
+                add_row<ATOMIC>(r1(tg[d - 1]), lane,
+                                make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w), out[d], on);
+            }
+        };
+        auto load_negs = [&](int32_t sub) {
+            const int32_t t_run = draw_sub(run, sub);
+            base_skip = 0xC0u;
 #pragma unroll
-        for (int d = 1; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
-        carried += (unsigned long long)(FN - __popc(base_skip & 0x3Eu));
+            for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_run, d);
+#pragma unroll
+            for (int d1 = 0; d1 < FN; ++d1)
+#pragma unroll
+                for (int d2 = d1 + 1; d2 < FN; ++d2) if (tg[d1] == tg[d2]) base_skip |= 2u << d2;   // repeated row: once
+#pragma unroll
+            for (int d = 0; d < FN; ++d)
+                out[d + 1] = (on && !((base_skip >> (d + 1)) & 1u)) ? ldcg4(r1(tg[d]), lane) : zero4;
+#pragma unroll
+            for (int d = 1; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
+            carried += (unsigned long long)(FN - __popc(base_skip & 0x3Eu));
+        };
+        load_negs(0);
         int32_t cur_c = -1, ahead_c = -1;
         float4 ahead = zero4;                                   // the next centre's row, read one pair early
         uint32_t skipmask = base_skip;
@@ -197,10 +225,17 @@ sgns_block_kernel(BlockArgs a)
             const int32_t qn = q + 1 < cnt ? q + 1 : q;
             const int32_t ctx_n = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.y, qn);
             const int32_t c_n = (int32_t)__shfl_sync(0xFFFFFFFFu, mine.x, qn);
+            if (a.cut == 2 && q > 0 && ((flags >> q) & 1u)) {    // a new negative group starts at this pair
+                flush_negs(); load_negs(q);
+                skipmask = base_skip;
+#pragma unroll
+                for (int d = 0; d < FN; ++d) if (tg[d] == cur_c) skipmask |= 2u << d;
+            }
             if (c != cur_c) {                                   // centre row: write back, take the next
                 if (cur_c >= 0) {
                     const float4 og = s_orig[wib][0][lane];
                     add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
+                    if (a.cut == 1) { flush_negs(); load_negs(q); ahead_c = -1; }
                 }
                 out[0] = ahead_c == c ? ahead : (on ? ldcg4(r1(c), lane) : zero4);
                 s_orig[wib][0][lane] = out[0];
@@ -213,7 +248,7 @@ sgns_block_kernel(BlockArgs a)
             // the next centre row and the next input row are read one pair early (no write of this warp
             // can hit the former before use; the latter is stale only if it is the row this pair updates)
             const bool stale = ctx_n == ctx;
-            if (c_n != c) { ahead = on ? ldcg4(r1(c_n), lane) : zero4; ahead_c = c_n; }
+            if (c_n != c && !a.cut) { ahead = on ? ldcg4(r1(c_n), lane) : zero4; ahead_c = c_n; }
             const float4 row1n = on ? ldcg4(r0(ctx_n), lane) : zero4;
 
             // 6 dot products by the transposing butterfly of the sentence-major kernel (n2v_sgns.cu)
@@ -254,13 +289,11 @@ sgns_block_kernel(BlockArgs a)
             ctx = ctx_n;
         }
         // one reduction per carried row: what this run added to it
-#pragma unroll
-        for (int d = 0; d <= FN; ++d) {
-            if (d == 0 ? (cur_c < 0) : ((base_skip >> d) & 1u)) continue;
-            const float4 og = s_orig[wib][d][lane];
-            add_row<ATOMIC>(r1(d == 0 ? cur_c : tg[d - 1]), lane,
-                            make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w), out[d], on);
+        if (cur_c >= 0) {
+            const float4 og = s_orig[wib][0][lane];
+            add_row<ATOMIC>(r1(cur_c), lane, make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
         }
+        flush_negs();
         pairs += (unsigned long long)cnt;
         __syncwarp();
     }
@@ -508,7 +541,7 @@ static int pairs_args(PairsArgs &g, const int32_t *tokens, const int64_t *sent_o
     N2V_REQUIRE(params, "params is NULL");
     N2V_REQUIRE(tokens && n_sent >= 0, "bad corpus");
     N2V_REQUIRE(sent_off || stride > 0, "sent_off is NULL and stride <= 0");
-    N2V_REQUIRE(params->window >= 1 && params->window <= 127, "window out of range");
+    N2V_REQUIRE(params->window >= 1 && params->window <= SGNS_MAX_WINDOW, "window out of range (1..96)");
     N2V_REQUIRE(params->max_sentence_len >= 1 && params->max_sentence_len <= 65535, "max_sentence_len out of range");
     const int lg = log2_parts(n_parts);
     N2V_REQUIRE(lg >= 0 && part >= 0 && part < n_parts, "n_parts must be 1, 2, 4 or 8 and 0 <= part < n_parts");
@@ -516,6 +549,7 @@ static int pairs_args(PairsArgs &g, const int32_t *tokens, const int64_t *sent_o
     g.a.tokens = tokens; g.a.sent_off = sent_off; g.a.n_sent = n_sent; g.a.stride = stride;
     g.a.sent_id_base = sent_id_base; g.a.vocab_of_id = vocab_of_id; g.a.keep_thr = keep_thr; g.a.p = *params;
     g.part = part; g.lg = lg; g.n_parts = n_parts;
+    g.neg_group = (params->tuning >> 8) & 0xFF;
     return N2V_OK;
 }
 
@@ -592,7 +626,7 @@ extern "C" int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const
     const int lg = log2_parts(n_parts);
     N2V_REQUIRE(lg >= 0 && part >= 0 && part < n_parts, "n_parts must be 1, 2, 4 or 8 and 0 <= part < n_parts");
     N2V_REQUIRE(params->V >= n_parts, "fewer vocabulary rows than parts");
-    N2V_REQUIRE(params->dim >= 1 && params->dim <= 128, "block kernel: dim must be <= 128");
+    N2V_REQUIRE(params->dim >= 4 && params->dim <= 128 && params->dim % 4 == 0, "block kernel: dim must be a multiple of 4, <= 128");
     N2V_REQUIRE(params->negative == BLK_FN, "block kernel: negative must be 5");
     N2V_REQUIRE(run_pairs >= 1 && run_pairs <= 32, "run_pairs must be in [1, 32]");
     N2V_REQUIRE(params->bucket_bits >= 0 && params->bucket_bits <= 24, "bucket_bits out of range");
@@ -610,7 +644,11 @@ extern "C" int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const
     const bool full = params->dim == 128;
     const bool reg_lookahead = (params->tuning & 1) != 0;     // 1: register look-ahead kernel (kept for comparison)
     const bool hot_private = (params->tuning & 2) != 0;       // 2: per-warp sums for the hottest input rows
-    if (params->atomic_updates && !reg_lookahead) {
+    // 4 (register look-ahead kernel only): a fresh negative set at every centre change, or -- when the pair
+    // streams carry group flags (bits 8-15 = G) -- at every flagged pair; 8: one contiguous range of runs per warp
+    a.cut = (params->tuning & 4) ? (((params->tuning >> 8) & 0xFF) ? 2 : 1) : 0;
+    a.blocked = (params->tuning & 8) ? 1 : 0;
+    if (params->atomic_updates && !reg_lookahead && !a.cut && !a.blocked) {
         if (full && hot_private) sgns_block_kernel_async<true, true, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         else if (full) sgns_block_kernel_async<true, true, false><<<blocks, SGNS_BLOCK, 0, stream>>>(a);
         else if (hot_private) sgns_block_kernel_async<true, false, true><<<blocks, SGNS_BLOCK, 0, stream>>>(a);

@@ -11,6 +11,9 @@ constexpr int MAX_EXP = 6;
 constexpr int SGNS_BLOCK = 128;          // 4 warps
 constexpr int SGNS_MAX_NEG = 16;
 constexpr int SGNS_SMEM_TOKENS = 256;    // per-warp staging of the kept tokens of a sentence chunk
+// next_chunk carries 2 * window kept tokens between chunks and load_chunk only appends while at most
+// SGNS_SMEM_TOKENS - 32 are staged: a larger window would never make progress
+constexpr int SGNS_MAX_WINDOW = (SGNS_SMEM_TOKENS - 32 - 32) / 2;   // 96
 
 // word2vec_inner.pyx init(): EXP_TABLE[i] = exp((i / 1000 * 2 - 1) * 6); then x / (x + 1), with the
 // Cython code's float32 casts (float argument, C double exp, float result, float division).

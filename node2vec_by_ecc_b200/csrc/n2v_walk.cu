@@ -87,7 +87,8 @@ walk_alias_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(WALK_BLOCK)
 walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                   const n2v_slot_t *__restrict__ node_slots, RejectParams rp, int symmetric,
+                   const n2v_slot_t *__restrict__ node_slots, const n2v_slot_t *__restrict__ first_slots,
+                   RejectParams rp, int symmetric,
                    const int32_t *__restrict__ starts, int64_t n_walks, int32_t L, uint32_t k0,
                    uint32_t k1, uint64_t walk_id_base, int32_t *__restrict__ walks,
                    int32_t *__restrict__ lens, unsigned long long *__restrict__ counters)
@@ -125,8 +126,11 @@ walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
                         if (u * (rp.bound * (double)K + rp.fold_mass) < rp.fold_mass) { nxt = prev; break; }
                     }
                     int64_t k = (int64_t)__umul64hi((uint64_t)r.x << 32, (uint64_t)K);   // floor(u*K)
-                    if (WEIGHTED) {   // static law ~ w(cur, .): the node alias table
-                        const uint2 sl = __ldg(reinterpret_cast<const uint2 *>(node_slots + b + k));
+                    // static law: the node alias table ~ w(cur, .) (weighted graphs / the popularity
+                    // edge law); the first step may have its own table (popularity node tables, :213-218)
+                    const n2v_slot_t *tab = (prev < 0 && first_slots) ? first_slots : (WEIGHTED ? node_slots : nullptr);
+                    if (tab) {
+                        const uint2 sl = __ldg(reinterpret_cast<const uint2 *>(tab + b + k));
                         if (!(r.y < sl.y)) k = (int64_t)(int32_t)sl.x;
                     }
                     const int32_t x = __ldg(col + b + k);
@@ -135,6 +139,7 @@ walk_reject_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restric
                     if (y < rp.t_lo) { nxt = x; break; }       // pre-accept: below every alpha
                     if (x == prev) { if (y < rp.t_ret) nxt = x; }
                     else if (y >= rp.t_hi) { /* pre-reject: above both remaining alphas */ }
+                    else if (rp.t_in == rp.t_out) { if (y < rp.t_in) nxt = x; }   // q == 1 / popularity law: no test
                     else {
                         ++n_tests;
                         n_probes += ceil_log2_p1(pe - pb);
@@ -205,23 +210,38 @@ extern "C" int n2v_walk_reject(const int64_t *row_ptr, const int32_t *col, const
                                uint64_t walk_id_base, int32_t *walks, int32_t *lens,
                                unsigned long long *counters, void *stream_)
 {
+    return n2v_walk_reject_law(row_ptr, col, w, node_slots, nullptr, p, q, symmetric, starts, n_walks, L, seed,
+                               walk_id_base, walks, lens, counters, stream_);
+}
+
+extern "C" int n2v_walk_reject_law(const int64_t *row_ptr, const int32_t *col, const double *w,
+                                   const n2v_slot_t *node_slots, const n2v_walk_law_t *law, double p, double q,
+                                   int symmetric, const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
+                                   uint64_t walk_id_base, int32_t *walks, int32_t *lens,
+                                   unsigned long long *counters, void *stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     N2V_REQUIRE(n_walks >= 0 && L >= 0, "negative size");
     N2V_REQUIRE(p > 0.0 && q > 0.0, "p and q must be positive");
     if (n_walks == 0 || L == 0) return N2V_OK;
     N2V_REQUIRE(row_ptr && col && starts && walks && lens, "NULL buffer");
-    N2V_REQUIRE(!w || node_slots, "weighted graph needs node_slots");
+    const bool pop_edges = law && law->pop_edges;
+    const n2v_slot_t *first_slots = law ? law->first_slots : nullptr;
+    N2V_REQUIRE(!(w || pop_edges) || node_slots, "weighted graph / popularity edge law needs node_slots");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    const RejectParams rp = make_reject_params(p, q, w != nullptr, symmetric);
+    // popularity edge law (node2vec.py:154-174): candidate ~ w / len(G[nbr]) from node_slots, alpha = 1/p on
+    // the return edge and 1 elsewhere (q is not used by the reference there); no folding (row sums unknown)
+    const RejectParams rp = pop_edges ? make_reject_params(p, 1.0, true, symmetric)
+                                      : make_reject_params(p, q, w != nullptr, symmetric);
     const int64_t blocks = (n_walks + WALK_BLOCK - 1) / WALK_BLOCK;
     N2V_REQUIRE(blocks < 2147483647ll, "too many walks for one launch");
-    if (w)
+    if (w || pop_edges)
         walk_reject_kernel<true><<<(unsigned)blocks, WALK_BLOCK, 0, stream>>>(
-            row_ptr, col, node_slots, rp, symmetric, starts, n_walks, L, (uint32_t)seed,
+            row_ptr, col, node_slots, first_slots, rp, symmetric, starts, n_walks, L, (uint32_t)seed,
             (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     else
         walk_reject_kernel<false><<<(unsigned)blocks, WALK_BLOCK, 0, stream>>>(
-            row_ptr, col, node_slots, rp, symmetric, starts, n_walks, L, (uint32_t)seed,
+            row_ptr, col, node_slots, first_slots, rp, symmetric, starts, n_walks, L, (uint32_t)seed,
             (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     N2V_LAUNCH_CHECK();
     return N2V_OK;

@@ -60,8 +60,8 @@ enum : int { ST_ROW = 0, ST_ALIAS = 1, ST_COL = 2, ST_PROBE = 3, ST_DONE = 4, ST
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(W2_BLOCK, N2V_W2_MINB)
 walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32_t *__restrict__ col,
-                           const n2v_slot_t *__restrict__ node_slots, const double *__restrict__ w,
-                           const double *__restrict__ strength,
+                           const n2v_slot_t *__restrict__ node_slots, const n2v_slot_t *__restrict__ first_slots,
+                           const double *__restrict__ w, const double *__restrict__ strength,
                            const unsigned long long *__restrict__ edge_hash, uint64_t hash_mask, RejectParams rp,
                            int64_t nnz, const int32_t *__restrict__ starts, int64_t n_walks, int32_t L, uint32_t k0,
                            uint32_t k1, uint64_t walk_id_base, int32_t *__restrict__ walks,
@@ -104,7 +104,8 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
         // ---- exactly one 8-byte load per lane, address by state
         unsigned long long v = 0;
         if (state == ST_ROW) v = __ldg(reinterpret_cast<const unsigned long long *>(packed_rows + cur));
-        else if (state == ST_ALIAS) v = __ldg(reinterpret_cast<const unsigned long long *>(node_slots + b + kk));
+        else if (state == ST_ALIAS)       // the first step may have its own table (popularity node tables)
+            v = __ldg(reinterpret_cast<const unsigned long long *>(((prev < 0 && first_slots) ? first_slots : node_slots) + b + kk));
         else if (state == ST_STR) v = __ldg(reinterpret_cast<const unsigned long long *>(strength + cur));
         else if (state == ST_WRET) v = __ldg(reinterpret_cast<const unsigned long long *>(w + slot));
         else if (state == ST_COL) {
@@ -133,6 +134,7 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
             else if (y_acc < rp.t_lo) accept = true;           // below every alpha
             else if (x == prev) { if (y_acc < rp.t_ret) accept = true; else draw = true; }
             else if (y_acc >= rp.t_hi) draw = true;            // above both remaining alphas
+            else if (rp.t_in == rp.t_out) { if (y_acc < rp.t_in) accept = true; else draw = true; }   // q == 1 / popularity law: no test
             else {
                 ++n_tests; n_probes += ceil_log2_p1(pdeg);
                 key = ((uint64_t)(uint32_t)x << 32) | (uint32_t)prev;   // G.has_edge(x, prev) (:144)
@@ -150,7 +152,7 @@ walk_reject_indexed_kernel(const uint64_t *__restrict__ packed_rows, const int32
             ++trial;
             y_acc = r.z; y_al = r.y;
             kk = (int64_t)__umul64hi((uint64_t)r.x << 32, (uint64_t)K);   // floor(u*K)
-            state = WEIGHTED ? ST_ALIAS : ST_COL;
+            state = (WEIGHTED || (prev < 0 && first_slots != nullptr)) ? ST_ALIAS : ST_COL;
             if (rp.fold && prev >= 0) {
                 // outlier: the return edge carries (1/p - B') extra area on top of the B'-high
                 // dartboard of K unit-weight columns; re-drawn every trial, always accepted.
@@ -234,25 +236,42 @@ extern "C" int n2v_walk_reject_indexed(const uint64_t *packed_rows, const int32_
                                        uint64_t walk_id_base, int32_t *walks, int32_t *lens,
                                        unsigned long long *counters, void *stream_)
 {
+    return n2v_walk_reject_indexed_law(packed_rows, col, nnz, w, strength, node_slots, nullptr, edge_hash, hash_capacity,
+                                       p, q, symmetric, starts, n_walks, L, seed, walk_id_base, walks, lens, counters,
+                                       stream_);
+}
+
+extern "C" int n2v_walk_reject_indexed_law(const uint64_t *packed_rows, const int32_t *col, int64_t nnz, const double *w,
+                                           const double *strength, const n2v_slot_t *node_slots, const n2v_walk_law_t *law,
+                                           const unsigned long long *edge_hash, uint64_t hash_capacity, double p, double q,
+                                           int symmetric, const int32_t *starts, int64_t n_walks, int32_t L, uint64_t seed,
+                                           uint64_t walk_id_base, int32_t *walks, int32_t *lens,
+                                           unsigned long long *counters, void *stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     N2V_REQUIRE(n_walks >= 0 && L >= 0, "negative size");
     N2V_REQUIRE(p > 0.0 && q > 0.0, "p and q must be positive");
     if (n_walks == 0 || L == 0) return N2V_OK;
     N2V_REQUIRE(packed_rows && col && edge_hash && starts && walks && lens, "NULL buffer");
     N2V_REQUIRE(hash_capacity >= 2 && (hash_capacity & (hash_capacity - 1)) == 0, "hash capacity must be a power of two");
-    N2V_REQUIRE(!w || node_slots, "weighted graph needs node_slots");
+    const bool pop_edges = law && law->pop_edges;
+    const n2v_slot_t *first_slots = law ? law->first_slots : nullptr;
+    N2V_REQUIRE(!(w || pop_edges) || node_slots, "weighted graph / popularity edge law needs node_slots");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
-    const RejectParams rp = make_reject_params(p, q, w != nullptr, symmetric, w != nullptr && strength != nullptr);
+    // popularity edge law (node2vec.py:154-174): candidate ~ w / len(G[nbr]) from node_slots, alpha = 1/p on
+    // the return edge and 1 elsewhere (q unused there); never folded (the row sums of w / pop are not supplied)
+    const RejectParams rp = pop_edges ? make_reject_params(p, 1.0, true, symmetric, false)
+                                      : make_reject_params(p, q, w != nullptr, symmetric, w != nullptr && strength != nullptr);
     const int64_t blocks = (n_walks + W2_BLOCK - 1) / W2_BLOCK;
     N2V_REQUIRE(blocks < 2147483647ll, "too many walks for one launch");
-    if (w)
+    if (w || pop_edges)
         walk_reject_indexed_kernel<true><<<(unsigned)blocks, W2_BLOCK, 0, stream>>>(
-            packed_rows, col, node_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
-            (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
+            packed_rows, col, node_slots, first_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L,
+            (uint32_t)seed, (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     else
         walk_reject_indexed_kernel<false><<<(unsigned)blocks, W2_BLOCK, 0, stream>>>(
-            packed_rows, col, node_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L, (uint32_t)seed,
-            (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
+            packed_rows, col, node_slots, first_slots, w, strength, edge_hash, hash_capacity - 1, rp, nnz, starts, n_walks, L,
+            (uint32_t)seed, (uint32_t)(seed >> 32), walk_id_base, walks, lens, counters);
     N2V_LAUNCH_CHECK();
     return N2V_OK;
 }

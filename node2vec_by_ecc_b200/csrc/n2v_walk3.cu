@@ -110,7 +110,8 @@ extern "C" int n2v_walk_alias_packed(const uint64_t *packed_rows, const n2v_slot
     N2V_REQUIRE(n_walks >= 0 && L >= 0, "negative size");
     if (n_walks == 0 || L == 0) return N2V_OK;
     N2V_REQUIRE(packed_rows && node_slots && starts && walks && lens, "NULL buffer");
-    N2V_REQUIRE(L <= 2 || (recs && edge_slots), "arc records / edge tables are NULL");
+    N2V_REQUIRE(L <= 1 || recs, "arc records are NULL");                  // read from the first step on
+    N2V_REQUIRE(L <= 2 || edge_slots, "edge tables are NULL");              // first used at the second step
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
     const int64_t blocks = (n_walks + W3_BLOCK - 1) / W3_BLOCK;
     N2V_REQUIRE(blocks < 2147483647ll, "too many walks for one launch");

@@ -30,6 +30,7 @@ class AliasTables:
     p: float = 1.0
     q: float = 1.0
     popwalk: bool = False
+    pop_edges: bool = False                   # edge law is get_alias_edge_pop (node2vec.py:154-174)
     packed_rows: torch.Tensor | None = None   # row_ptr << 24 | deg per node
     arc_recs: torch.Tensor | None = None      # int64[nnz, 4]: one 32-byte record per arc
 
@@ -173,7 +174,7 @@ class DeviceGraph:
         L = lib()
         dev = self.device
         t = self.build_node_tables(popwalk=popwalk, keep_raw=keep_raw)
-        t.p, t.q = float(p), float(q)
+        t.p, t.q, t.pop_edges = float(p), float(q), bool(pop_edges)
         etab = self.etab_offsets()
         total = self.sum_deg_sq()
         t.etab_ptr = etab
@@ -261,30 +262,59 @@ class DeviceGraph:
 
     def walk_reject(self, p: float, q: float, starts: torch.Tensor, L_: int, seed: int,
                     walk_id_base: int = 0, node_tables: AliasTables | None = None, counters=None,
-                    out=None, indexed: bool = True):
+                    out=None, indexed: bool = True, first_tables: AliasTables | None = None,
+                    pop_edges: bool = False):
         """Same law as get_alias_edge (node2vec.py:142-150) by rejection sampling; no edge tables.
         indexed=True uses the hashed distance-1 test + per-lane state machine (n2v_walk_reject_indexed,
-        16 bytes per arc of index), False the binary-search form (n2v_walk_reject, no extra memory)."""
+        16 bytes per arc of index), False the binary-search form (n2v_walk_reject, no extra memory).
+        node_tables: the candidate law of steps >= 2 (plain weights; built here when missing on a
+        weighted graph). first_tables: table of the first step when it differs (the popularity node
+        tables, node2vec.py:213-218). pop_edges: steps >= 2 follow get_alias_edge_pop (:154-174);
+        node_tables must then be built over w / len(G[nbr]) for every node (pop_all_node_tables)."""
         starts = torch.as_tensor(starts, dtype=torch.int32).to(self.device).contiguous()
         n = int(starts.shape[0])
+        if pop_edges and node_tables is None:
+            node_tables = self.pop_all_node_tables()
         if self.w is not None and node_tables is None:
             node_tables = self.build_node_tables()
+        law = None
+        if first_tables is not None or pop_edges:
+            from ._lib import WalkLaw
+            law = WalkLaw(C.c_void_p(first_tables.node_slots.data_ptr() if first_tables is not None else 0),
+                          C.c_int32(int(bool(pop_edges))))
+            law = C.byref(law)
         walks, lens = out if out is not None else (
             torch.empty((n, L_), dtype=torch.int32, device=self.device),
             torch.empty(n, dtype=torch.int32, device=self.device))
         rix = self.reject_index() if indexed else None
         if rix is not None:
             packed, table, cap, strength = rix
-            check(lib().n2v_walk_reject_indexed(
+            check(lib().n2v_walk_reject_indexed_law(
                 ptr(packed), ptr(self.col), C.c_int64(self.nnz), ptr(self.w), ptr(strength),
-                ptr(node_tables.node_slots if node_tables is not None else None), ptr(table), C.c_uint64(cap),
+                ptr(node_tables.node_slots if node_tables is not None else None), law, ptr(table), C.c_uint64(cap),
                 C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts), C.c_int64(n),
                 C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base), ptr(walks), ptr(lens), ptr(counters),
                 stream()))
             return walks, lens
-        check(lib().n2v_walk_reject(ptr(self.row_ptr), ptr(self.col), ptr(self.w),
-                                    ptr(node_tables.node_slots if node_tables is not None else None),
-                                    C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts),
-                                    C.c_int64(n), C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base),
-                                    ptr(walks), ptr(lens), ptr(counters), stream()))
+        check(lib().n2v_walk_reject_law(ptr(self.row_ptr), ptr(self.col), ptr(self.w),
+                                        ptr(node_tables.node_slots if node_tables is not None else None), law,
+                                        C.c_double(p), C.c_double(q), C.c_int(int(self.symmetric)), ptr(starts),
+                                        C.c_int64(n), C.c_int32(L_), C.c_uint64(seed), C.c_uint64(walk_id_base),
+                                        ptr(walks), ptr(lens), ptr(counters), stream()))
         return walks, lens
+
+    def plain_node_tables(self) -> AliasTables:
+        if "plain_nodes" not in self._cache:
+            self._cache["plain_nodes"] = self.build_node_tables()
+        return self._cache["plain_nodes"]
+
+    def pop_all_node_tables(self) -> AliasTables:
+        """node tables over w / len(G[nbr]) for EVERY node: the candidate law of get_alias_edge_pop
+        (node2vec.py:154-174, which -- unlike the node law :213-218 -- has no item exception)."""
+        if "popall" not in self._cache:
+            item, self.is_item = self.is_item, None
+            try:
+                self._cache["popall"] = self.build_node_tables(popwalk=True)
+            finally:
+                self.is_item = item
+        return self._cache["popall"]

@@ -192,14 +192,28 @@ class Graph:
         self._dg_for = None
         self._tables = None
         self._tables_raw = None
+        self._prep = None                 # which preprocess_* was called: None | "plain" | "pop" (picklable)
+        self._otf_key = None
         self._walk_id_base = 0
 
-    # Graph instances are pickled to pool workers by main_link.py:277; device handles stay behind.
+    # Graph instances are pickled to pool workers by main_link.py:277 -- after preprocess_* ran in the
+    # parent (:216-226). Device handles stay behind; the worker rebuilds the tables it needs lazily
+    # from `_prep`, and takes a walk-id range of its own (the reference's workers all inherit one numpy
+    # RNG state; here equal ids would mean equal Philox streams).
     def __getstate__(self):
         st = dict(self.__dict__)
-        for k in ("_dg_obj", "_dg_for", "_tables", "_tables_raw"):
-            st[k] = None
+        for k in ("_dg_obj", "_dg_for", "_tables", "_tables_raw", "alias_nodes", "alias_edges"):
+            st.pop(k, None)
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._dg_obj = self._dg_for = self._tables = self._tables_raw = None
+        self._otf_key = None
+        self._walk_id_base += (os.getpid() & 0xFFFFF) << 40
+        if self._prep is not None:
+            self.alias_nodes = _TableView(self, edges=False)
+            self.alias_edges = _TableView(self, edges=True)
 
     # ---- device graph, rebuilt when the caller swaps/mutates self.G (main_link.py:592) ----------
     @property
@@ -209,6 +223,7 @@ class Graph:
             self._dg_obj = DeviceGraph.from_networkx(self.G)
             self._dg_for = key
             self._tables = self._tables_raw = None
+            self._otf_key = None
             self._index_map = {l: i for i, l in enumerate(self._dg_obj.labels.tolist())}
         return self._dg_obj
 
@@ -239,26 +254,35 @@ class Graph:
 
     def _raw_tables(self) -> AliasTables:
         if self._tables_raw is None:
-            pop = bool(self._tables.popwalk) if self._tables is not None else False
-            self._tables_raw = self._build(pop, edges=True, keep_raw=True)
+            self._tables_raw = self._build(self._prep == "pop", edges=True, keep_raw=True)
         return self._tables_raw
+
+    def _prepared(self) -> AliasTables:
+        """the tables of the preprocess_* call on record (rebuilt after unpickling / a swap of self.G)"""
+        self._dg
+        if self._tables is None or self._otf_key is not None:
+            if self._prep is None:
+                raise AttributeError("'Graph' object has no attribute 'alias_nodes' "
+                                     "(call preprocess_transition_probs() first)")
+            self._tables = self._build(self._prep == "pop", edges=self._use_alias())
+            self._otf_key = None
+        return self._tables
 
     # ---- reference API ---------------------------------------------------------------------------
     def preprocess_transition_probs(self):
         """node2vec.py:176-204. Node tables always; edge tables when they fit (else the walks use
         the rejection sampler, which needs none)."""
-        self._otf_key = None
-        self._tables = self._build(False, edges=self._use_alias())
-        self._tables_raw = None
+        self._prep, self._tables, self._tables_raw = "plain", None, None
+        self._prepared()
         self.alias_nodes = _TableView(self, edges=False)
         self.alias_edges = _TableView(self, edges=True)
         return
 
     def preprocess_transition_probs_popularity(self):
-        """node2vec.py:206-237: popularity-normalised node tables, plain edge tables (:228-232)."""
-        self._otf_key = None
-        self._tables = self._build(True, edges=self._use_alias())
-        self._tables_raw = None
+        """node2vec.py:206-237: popularity-normalised node tables (first step), plain edge law
+        (:228-232) -- as edge tables when they fit, else by rejection."""
+        self._prep, self._tables, self._tables_raw = "pop", None, None
+        self._prepared()
         self.alias_nodes = _TableView(self, edges=False)
         self.alias_edges = _TableView(self, edges=True)
         return
@@ -284,30 +308,37 @@ class Graph:
         if tables.edge_slots is not None:
             walks, lens = dg.walk_alias(tables, starts, int(walk_length), self.seed, base)
         else:
+            # rejection mode. The candidate law of steps >= 2 is the PLAIN weight row (a node table on
+            # weighted graphs, uniform otherwise); popularity node tables only ever drive the first step
+            # (node2vec.py:69-70 with :213-218), unless the whole edge law is get_alias_edge_pop.
+            pop_edges = bool(getattr(tables, "pop_edges", False))
+            first = tables if tables.popwalk else None
+            plain = None
+            if not pop_edges and dg.w is not None:
+                plain = tables if not tables.popwalk else dg.plain_node_tables()
             walks, lens = dg.walk_reject(float(self.p), float(self.q), starts, int(walk_length), self.seed,
-                                         base, node_tables=tables)
+                                         base, node_tables=plain, first_tables=first, pop_edges=pop_edges)
         return WalkCorpus(walks, lens, dg.labels)
 
     def simulate_walks(self, num_walks, walk_length, nodes=None, verbose=False):
         """node2vec.py:81-95."""
-        if getattr(self, "_tables", None) is None:
-            raise AttributeError("'Graph' object has no attribute 'alias_nodes' "
-                                 "(call preprocess_transition_probs() first)")
-        return self._simulate(num_walks, walk_length, nodes, self._tables, verbose)
+        return self._simulate(num_walks, walk_length, nodes, self._prepared(), verbose)
 
     def simulate_walks_on_the_fly(self, num_walks, walk_length, nodes=None, verbose=False):
         """node2vec.py:97-111: same walks without a prior preprocess call. popwalk "pop" follows
         get_alias_nodes_cur / get_alias_edge_pop (:13-32,:154-174), whose edge law ignores q."""
         pop = self.popwalk == "pop"
         key = ("otf", float(self.p), float(self.q), pop)
+        self._dg
+        if self._prep == "plain" and not pop and self._tables is not None and self._otf_key is None:
+            return self._simulate(num_walks, walk_length, nodes, self._tables, verbose)   # same law, tables at hand
         if self._tables is None or getattr(self, "_otf_key", None) != key:
             dg = self._dg
-            if pop:
-                # popularity law: tables only (its rejection form is not built); they must fit
-                if dg.edge_table_bytes() * 2.5 > self._table_budget() and self.mode != "alias":
-                    raise NotImplementedError("popwalk='pop' needs edge alias tables and they do not fit "
-                                              "N2V_TABLE_BUDGET_GB on this graph")
+            if pop and self._use_alias():
                 self._tables = dg.build_alias_tables(float(self.p), float(self.q), popwalk=True, pop_edges=True)
+            elif pop:             # get_alias_edge_pop by rejection: popularity node tables + the w/pop candidate law
+                self._tables = dg.build_node_tables(popwalk=True)
+                self._tables.pop_edges = True
             else:
                 self._tables = self._build(False, edges=self._use_alias())
             self._tables_raw = None
@@ -323,6 +354,4 @@ class Graph:
 
     def get_alias_edge(self, src, dst):
         """node2vec.py:133-152 -> (J, q) of one arc."""
-        if self._tables is None:
-            self._tables = self._build(False, edges=True)
         return _TableView(self, edges=True)[(src, dst)]

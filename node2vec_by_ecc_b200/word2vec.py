@@ -284,6 +284,8 @@ class PeerSgnsTrainer(SgnsTrainer):
         if self.n_parts not in (1, 2, 4, 8):
             raise ValueError("the tables can be spread over 1, 2, 4 or 8 parts")
         super().__init__(counts_by_id, *args, **kw)
+        if self.dim % 4 or self.dim > 128:
+            raise ValueError("sharded tables need dim to be a multiple of 4, <= 128")
 
     def reset_weights(self):
         from . import dist as D
@@ -382,6 +384,8 @@ class BlockSgnsTrainer(SgnsTrainer):
         super().__init__(counts_by_id, *args, **kw)
         if self.V < self.n_parts:
             raise ValueError("fewer vocabulary rows than parts")
+        if self.dim % 4 or self.dim > 128:
+            raise ValueError("block-partitioned tables need dim to be a multiple of 4, <= 128")
 
     @property
     def _mine(self):

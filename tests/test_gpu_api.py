@@ -79,6 +79,53 @@ def test_graph_survives_pickle():
     G.preprocess_transition_probs()
     G2 = pickle.loads(pickle.dumps(G))
     assert len(G2.simulate_walks_on_the_fly(1, 10)) == 34
+    # main_link.py:216-226,:277-296: preprocess in the parent, node2vec_walk / simulate_walks in the
+    # pool workers -- the unpickled copy rebuilds the tables of the preprocess call on record
+    G3 = pickle.loads(pickle.dumps(G))
+    w = G3.node2vec_walk(walk_length=12, start_node=1)
+    assert len(w) == 12 and w[0] == 1
+    assert len(G3.simulate_walks(2, 10, nodes=[1, 2, 3])) == 6
+    J, q = G3.alias_edges[(1, 2)]
+    J0, q0 = G.alias_edges[(1, 2)]
+    assert (J == J0).all() and (q == q0).all()
+    assert G3._walk_id_base != G._walk_id_base            # workers do not reuse the parent's Philox streams
+    # the popularity variant survives too, and a Graph that was never preprocessed still refuses
+    Gp = Graph(karate_nx(), False, 1, 1, popwalk="pop")
+    Gp.preprocess_transition_probs_popularity()
+    Gp2 = pickle.loads(pickle.dumps(Gp))
+    assert Gp2._prep == "pop" and len(Gp2.simulate_walks(1, 10)) == 34
+    import pytest
+    with pytest.raises(AttributeError):
+        pickle.loads(pickle.dumps(Graph(karate_nx(), False, 1, 1))).simulate_walks(1, 5)
+
+
+def test_popularity_walks_in_rejection_mode_follow_the_reference_laws():
+    """popwalk="pop" on a graph whose edge tables "do not fit" (mode="reject"): both entry points of
+    main_link.py:206-219,:274-281 run, produce only arcs, and follow the popularity node law on the
+    first step (chi-square; the edge laws are tested through DeviceGraph in test_gpu_walks.py)."""
+    import numpy as np
+    from helpers import chi_square_p
+    from node2vec_by_ecc_b200 import Graph
+    import networkx as nx
+    rng = np.random.RandomState(3)
+    G = nx.Graph()
+    users, items = list(range(1, 41)), [int("9999999" + str(i)) for i in range(30)]
+    for u in users:
+        for it in rng.choice(items, size=rng.randint(2, 12), replace=False):
+            G.add_edge(u, int(it), weight=int(rng.randint(1, 4)))
+    g = Graph(G, False, 0.5, 2.0, popwalk="pop", mode="reject", seed=5)
+    g.preprocess_transition_probs_popularity()
+    assert g._tables.edge_slots is None
+    for walks in (g.simulate_walks(200, 6), g.simulate_walks_on_the_fly(200, 6)):
+        assert len(walks) == 200 * G.number_of_nodes()
+        for w in walks[:300]:
+            assert all(G.has_edge(a, b) for a, b in zip(w[:-1], w[1:]))
+    # first step from user 1: weight / len(G[nbr]) (node2vec.py:213-218)
+    nbrs = sorted(G.neighbors(1))
+    pr = np.asarray([G[1][x]["weight"] / len(G[x]) for x in nbrs], dtype=np.float64)
+    walks = g.simulate_walks(20000, 2, nodes=[1])
+    obs = np.bincount([nbrs.index(w[1]) for w in walks], minlength=len(nbrs))
+    assert chi_square_p(obs, pr / pr.sum()) > 1e-4
 
 
 def golden_nx(name):

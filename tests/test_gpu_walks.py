@@ -197,3 +197,98 @@ def test_alias_and_rejection_agree_on_visit_frequencies():
     fr = visit_law(dg.walk_reject(0.25, 4.0, starts, 40, seed=2)[0])
     noise = np.abs(fa1 - fa2).sum()           # sampling noise of the statistic: alias vs alias
     assert np.abs(fa1 - fr).sum() < 1.5 * noise and np.abs(fa2 - fr).sum() < 1.5 * noise
+
+
+def alias_table_probs(J, q):
+    """the distribution an alias table (J, q) samples: p[k] = (q[k] + sum_{j: J[j]=k} (1 - q[j])) / K"""
+    K = len(J)
+    pr = np.minimum(q, 1.0).copy()
+    np.add.at(pr, J, 1.0 - np.minimum(q, 1.0))
+    return pr / K
+
+
+@pytest.mark.parametrize("weighted,p", [(False, 0.25), (True, 0.5), (False, 4.0)])
+@pytest.mark.parametrize("indexed", [True, False])
+def test_popularity_rejection_walker_chi_square(weighted, p, indexed):
+    """popwalk="pop" without edge tables (the graphs run_all_ue_pop.sh targets do not fit them):
+    first step ~ get_alias_nodes_cur (node2vec.py:13-25, item rows plain), later steps ~
+    get_alias_edge_pop (:154-174) -- chi-square against the oracle's exact popularity tables."""
+    n = 300
+    _, g = random_graph(n, 3000, seed=37, weighted=weighted, skew=1.0)
+    is_item = (np.arange(n) % 3 == 0).astype(np.uint8)           # "9999999"-prefixed labels
+    dg = dev_graph(g, symmetric=True, is_item=is_item)
+    hub = int(np.argmax(np.diff(g.row_ptr)))
+    starts_np = np.concatenate([np.full(400000, hub, dtype=np.int32), np.repeat(np.arange(n, dtype=np.int32), 2000)])
+    first = dg.build_node_tables(popwalk=True)
+    walks, lens = dg.walk_reject(p, 4.0, torch.as_tensor(starts_np), 3, seed=12, indexed=indexed,
+                                 first_tables=first, pop_edges=True)
+    w = walks.cpu().numpy()
+    # first step: popularity node law (w / deg(nbr) unless the node is an item)
+    to = oracle.preprocess(g, p, 4.0, is_item=is_item, popwalk_nodes=True)
+    for v in (hub, 3, 4):
+        a, b = g.row_ptr[v], g.row_ptr[v + 1]
+        if b - a < 2:
+            continue
+        row = g.col[a:b]
+        sel = w[:, 0] == v
+        obs = np.bincount(np.searchsorted(row, w[sel, 1]), minlength=len(row))
+        assert chi_square_p(obs, alias_table_probs(to.nJ[a:b], to.nq[a:b])) > 1e-4
+    # later steps: get_alias_edge_pop rows
+    keys, c = transition_counts(walks, lens, n)
+    a_, b_, nxt = keys // (n * n), (keys // n) % n, keys % n
+    pair = a_ * n + b_
+    sums = {}
+    for pk, cc in zip(pair, c):
+        sums[pk] = sums.get(pk, 0) + cc
+    pvals = []
+    for pk in sorted(sums, key=lambda k: -sums[k])[:40]:
+        aa, bb = int(pk // n), int(pk % n)
+        J, qq = oracle.edge_table(g, p, 4.0, aa, bb, popwalk=True)
+        row = g.col[g.row_ptr[bb]:g.row_ptr[bb + 1]]
+        obs = np.zeros(len(row))
+        sel = pair == pk
+        obs[np.searchsorted(row, nxt[sel])] = c[sel]
+        pvals.append(chi_square_p(obs, alias_table_probs(J, qq)))
+    pvals = np.asarray(pvals)
+    assert pvals.min() > 1e-5 and (pvals < 0.01).sum() <= 3, np.sort(pvals)[:6]
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_popularity_preprocess_rejection_first_step_then_plain_law(weighted):
+    """preprocess_transition_probs_popularity + rejection mode (node2vec.py:206-237): the first step
+    follows the popularity node table, later steps the PLAIN get_alias_edge law (:228-232)."""
+    n = 300
+    _, g = random_graph(n, 3000, seed=39, weighted=weighted, skew=1.0)
+    is_item = (np.arange(n) % 2 == 0).astype(np.uint8)
+    dg = dev_graph(g, symmetric=True, is_item=is_item)
+    hub = int(np.argmax(np.diff(g.row_ptr)))
+    hub = hub if not is_item[hub] else int(np.argsort(np.diff(g.row_ptr) * (1 - is_item))[-1])
+    starts_np = np.concatenate([np.full(400000, hub, dtype=np.int32), np.repeat(np.arange(n, dtype=np.int32), 1000)])
+    first = dg.build_node_tables(popwalk=True)
+    walks, lens = dg.walk_reject(0.25, 4.0, torch.as_tensor(starts_np), 3, seed=13, first_tables=first)
+    w = walks.cpu().numpy()
+    to = oracle.preprocess(g, 0.25, 4.0, is_item=is_item, popwalk_nodes=True)
+    a, b = g.row_ptr[hub], g.row_ptr[hub + 1]
+    row = g.col[a:b]
+    sel = w[:, 0] == hub
+    obs = np.bincount(np.searchsorted(row, w[sel, 1]), minlength=len(row))
+    assert chi_square_p(obs, alias_table_probs(to.nJ[a:b], to.nq[a:b])) > 1e-4
+    plain = oracle.transition_row(g, 1.0, 1.0, -1, hub)
+    assert np.abs(plain - alias_table_probs(to.nJ[a:b], to.nq[a:b])).max() > 1e-3     # the two laws differ here
+    keys, c = transition_counts(walks, lens, n)
+    a_, b_, nxt = keys // (n * n), (keys // n) % n, keys % n
+    pair = a_ * n + b_
+    sums = {}
+    for pk, cc in zip(pair, c):
+        sums[pk] = sums.get(pk, 0) + cc
+    pvals = []
+    for pk in sorted(sums, key=lambda k: -sums[k])[:30]:
+        aa, bb = int(pk // n), int(pk % n)
+        probs = oracle.transition_row(g, 0.25, 4.0, aa, bb)
+        row = g.col[g.row_ptr[bb]:g.row_ptr[bb + 1]]
+        obs = np.zeros(len(row))
+        sel = pair == pk
+        obs[np.searchsorted(row, nxt[sel])] = c[sel]
+        pvals.append(chi_square_p(obs, probs))
+    pvals = np.asarray(pvals)
+    assert pvals.min() > 1e-5 and (pvals < 0.01).sum() <= 3, np.sort(pvals)[:6]
