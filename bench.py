@@ -75,7 +75,9 @@ def parse():
                          "buckets per sub-step, syn0 parts passed round a ring (no replicas); peer = one table pair "
                          "sharded over the GPUs' HBM, trained over NVLink peer memory; replica = a full copy per GPU, "
                          "delta-sum all-reduce every --sync-walks")
-    ap.add_argument("--run-pairs", type=int, default=32, help="block mode: pairs sharing one negative set")
+    ap.add_argument("--neg-group", type=int, default=1,
+                    help="block mode: token positions of a walk whose centres share one negative set (1 = one set per "
+                         "centre occurrence, the single-GPU law)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -139,8 +141,8 @@ def config_of(a, n_nodes=None, nnz=None):
                      f"p={a.p} q={a.q}, R={a.num_walks} L={a.walk_length}; SGNS d={a.dim} window={a.window} "
                      f"negative={a.negative} sample=1e-3",
          "batch_walks_per_gpu": a.batch_walks, "generator": "node2vec_by_ecc_b200.synth.rmat_edges seed=1",
-         "sgns_negatives": ("one set of 5 per run of %d consecutive pairs of a (centre part, context part) bucket" % a.run_pairs
-                            if (a.shared_negatives and a.gpus > 1 and a.multi_gpu_sgns == "block") else
+         "sgns_negatives": ("one set of 5 per %d consecutive centre positions of a walk, shared by their context pairs" % a.neg_group
+                            if (a.shared_negatives and a.gpus > 1 and a.multi_gpu_sgns == "block" and a.neg_group > 1) else
                             "one set of 5 per centre, shared by its context pairs (other_negative_mode = fresh set per pair)"
                             if a.shared_negatives else "fresh set of 5 per (centre, context) pair, gensim's law"),
          "l2": "inputs larger than L2 (no flush)"}
@@ -208,7 +210,7 @@ def run_ours(a):
     if block:     # tables cut into `world` row sets; orthogonal pair buckets; syn0 parts round a ring
         from node2vec_by_ecc_b200 import BlockSgnsTrainer
         trainer = BlockSgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1,
-                                   run_pairs=a.run_pairs)
+                                   neg_group=a.neg_group)
     elif peer:    # ONE table pair spread over the GPUs' HBM, trained by all of them over NVLink
         from node2vec_by_ecc_b200 import PeerSgnsTrainer
         trainer = PeerSgnsTrainer(counts, dim=a.dim, window=a.window, negative=a.negative, sample=1e-3, seed=1)
@@ -253,7 +255,8 @@ def run_ours(a):
             e2.record()
             if block:     # one pool = this step's walks of all ranks (rank order = global walk id order)
                 trainer.train(walks, None, B, L, total_examples=total_walks, example_base=(i * world * B) % total_walks,
-                              sent_id_base=i * world * B, grid_warps=a.hogwild_warps or None)
+                              sent_id_base=i * world * B, sent_per_job=10000 // L, grid_warps=a.hogwild_warps or None,
+                              exact_bounds=False)
             else:
                 trainer.train(walks[sa:sb_], None, sb_ - sa, L, total_examples=total_walks,
                               example_base=(g0 + sa) % total_walks, sent_id_base=g0 + sa, sent_per_job=10000 // L,
@@ -356,7 +359,7 @@ def run_ours(a):
             # block kernel: per pair the input row, per carried output row (centre changes + the 5
             # negatives of a run) one read + one reduction: 1,024 B each; `centres` = carried rows
             alg_bytes = (my_pairs_rank + centres / world) * 1024.0
-            kname = "sgns_block_kernel (one negative set per run of %d pairs)" % a.run_pairs
+            kname = "sgns_group_kernel (block-partitioned tables, neg_group %d)" % a.neg_group
             k_ms = phases["train"]
         elif a.shared_negatives:
             # shared-negative kernel: per pair the input row (read + written, 1,024 B), per centre
@@ -405,7 +408,7 @@ def run_ours(a):
                            "4 B/token); GPU k expands the pairs whose centre is in part k, bucketed by the context's part, and "
                            "trains bucket (k, (k + e) % N) in sub-step e against syn1neg part k and the syn0 part it holds, "
                            "which then moves to GPU k - 1 (NCCL send/recv ring); no replicas, no averaging",
-                 "run_pairs": a.run_pairs, "pool_walks": B * world} if block else
+                 "neg_group": a.neg_group, "pool_walks": B * world} if block else
                 {"tables": "one syn0/syn1neg pair, row i in GPU i % N's HBM, every GPU trains its own walks against all parts "
                            "over NVLink peer memory (red.global.add.v4.f32); no replicas, no sync"} if peer else
                 {"tables": "replicated; delta-sum all-reduce of syn0 and syn1neg", "walks_per_gpu_per_sync": sync_walks,

@@ -243,41 +243,50 @@ int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64
                            unsigned long long *pairs_out, void *stream);
 
 /* Block-partitioned training (the multi-GPU form of learn_embeddings, src/main.py:82-90; same
- * per-pair arithmetic as n2v_sgns_train). Tables in n_parts row sets as above. A pool of walks is
- * expanded into (centre, context) pairs; the pairs whose centre is in part `part` are written as
- * n_parts streams, stream b = pairs whose context is in part b, each pair int32 {centre local row,
- * context local row}. Stream (part, b) touches only syn1neg part `part` and syn0 part b, so GPU k
- * trains stream (k, (k + e) % n_parts) in sub-step e and the syn0 parts travel round a ring: no row
- * is replicated, nothing is averaged.
- *   n2v_sgns_pairs_count: offsets int64[n_parts * n_sent + 1], exclusive scan of the per-(stream,
- *       sentence) pair counts in stream-major order: stream b = pairs [offsets[b * n_sent],
+ * per-pair arithmetic and the same negative law as n2v_sgns_train with negative_sharing = 1).
+ * Tables in n_parts row sets as above. A pool of walks is expanded into (centre, context) pairs;
+ * the pairs whose centre is in part `part` are written as n_parts streams, stream b = pairs whose
+ * context is in part b. Stream (part, b) touches only syn1neg part `part` and syn0 part b, so GPU
+ * k trains stream (k, (k + e) % n_parts) in sub-step e and the syn0 parts travel round a ring: no
+ * row is replicated, nothing is averaged.
+ * Stream format, uint32 words: the pairs of one centre occurrence inside a stream are a GROUP =
+ * {0x80000000 | centre local row, sentence index within this call, token position | pairs << 16}
+ * followed by one word per pair (the context's local row); only a group's first word has bit 31 set.
+ *   n2v_sgns_groups_count: offsets int64[n_parts * n_sent + 1], exclusive scan of the per-(stream,
+ *       sentence) word counts in stream-major order: stream b = words [offsets[b * n_sent],
  *       offsets[(b + 1) * n_sent]); the last entry is the total.
- *   n2v_sgns_pairs_fill: writes the pairs (order: stream, sentence, centre, context); pairs beyond
- *       capacity_pairs are dropped and counted in *overflow (device uint64).
- *   n2v_sgns_train_block: trains pairs[0, n_pairs) of one stream against (syn0 part of the stream's
- *       contexts, syn1neg part `part`). One set of 5 negatives per run of run_pairs (<= 32)
- *       consecutive pairs, Philox ctr (run, tag, epoch), each draw mapped to the word of the same
- *       local row in `part`; a row repeated in the set is used once, a negative equal to a pair's
- *       centre is skipped for that pair. alpha is the caller's (one value per call). Uses params->
- *       V, dim (<= 128), negative (5), bucket_bits, seed, epoch, grid_warps, atomic_updates, tuning
- *       (experiment switches, 0 = default: bit 0 register look-ahead kernel, bit 1 per-warp sums for
- *       the hottest input rows).
- *       pairs_out[0] += pairs, [1] += output rows carried in registers (centre changes + the
- *       negatives of every run): algorithmic bytes = 1,024 * (pairs + carried rows) at dim 128. */
-size_t n2v_sgns_pairs_workspace_bytes(int64_t n_sent, int32_t n_parts);
-int n2v_sgns_pairs_count(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
+ *   n2v_sgns_groups_fill: writes the words (order: stream, sentence, centre, context); words beyond
+ *       capacity_words are dropped and counted in *overflow (device uint64).
+ *   n2v_sgns_train_groups: trains the stream words[first_word, first_word + n_words) -- or, when
+ *       dev_first / dev_end are given, [*dev_first, *dev_end) read on the device (two entries of
+ *       `offsets`; no host round trip), clamped to capacity_words -- against (syn0 part of the
+ *       stream's contexts, syn1neg part `part`). Every warp takes one contiguous range of whole
+ *       groups. Negatives: ONE set of 5 per centre occurrence, Philox ctr (sent_id_base + sentence
+ *       index, position << 16 | 0xFFFF, epoch) -> count^0.75 table, i.e. the very draws n2v_sgns_train
+ *       makes for that centre, each mapped to the word of the same local row in `part`; a negative
+ *       equal to the centre is skipped, a set with a repeated row runs pair by pair with gensim's
+ *       sequential semantics. neg_group = G > 1: the centres at G consecutive token positions of a
+ *       sentence share one set (position / G in the counter). alpha follows the sentence's job
+ *       (params->alpha0, min_alpha, total_examples, example_base, sent_per_job) as in n2v_sgns_train.
+ *       Also uses params->V, dim (<= 128, % 4), negative (5), bucket_bits, seed, epoch, grid_warps,
+ *       atomic_updates. pairs_out[0] += pairs, [1] += output rows carried in registers (one centre
+ *       row per group + 5 per negative set): algorithmic bytes = 1,024 * (pairs + carried rows). */
+size_t n2v_sgns_groups_workspace_bytes(int64_t n_sent, int32_t n_parts);
+int n2v_sgns_groups_count(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
+                          int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
+                          const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
+                          int64_t *offsets, void *workspace, size_t workspace_bytes, void *stream);
+int n2v_sgns_groups_fill(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
                          int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
                          const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
-                         int64_t *offsets, void *workspace, size_t workspace_bytes, void *stream);
-int n2v_sgns_pairs_fill(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
-                        int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
-                        const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
-                        const int64_t *offsets, int32_t *pairs, int64_t capacity_pairs,
-                        unsigned long long *overflow, void *stream);
-int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const uint32_t *cum_table,
-                         const int32_t *bucket_lo, const n2v_sgns_params_t *params, float alpha,
-                         int32_t run_pairs, uint32_t tag, float *syn0_part, float *syn1neg_part,
-                         int32_t part, int32_t n_parts, unsigned long long *pairs_out, void *stream);
+                         const int64_t *offsets, uint32_t *words, int64_t capacity_words,
+                         unsigned long long *overflow, void *stream);
+int n2v_sgns_train_groups(const uint32_t *words, int64_t first_word, int64_t n_words,
+                          const int64_t *dev_first, const int64_t *dev_end, int64_t capacity_words,
+                          int64_t sent_id_base, const uint32_t *cum_table, const int32_t *bucket_lo,
+                          const n2v_sgns_params_t *params, int32_t neg_group, float *syn0_part,
+                          float *syn1neg_part, int32_t part, int32_t n_parts,
+                          unsigned long long *pairs_out, void *stream);
 
 /* ---- link scoring ---------------------------------------------------------------------------
  * replaces: link_score(emb, a, b) with link_method "cos" (src/main_link.py:43-49) over a batch of
@@ -285,6 +294,28 @@ int n2v_sgns_train_block(const int32_t *pairs, int64_t n_pairs, const uint32_t *
  * score 0, the reference's except branch). emb float32[V, dim], dim % 4 == 0. */
 int n2v_cosine_pairs(const float *emb, int32_t dim, const int32_t *a, const int32_t *b,
                      int64_t n_pairs, float *out, void *stream);
+
+/* All-pairs similarity with the selection fused in -- link_prediction / make_links_and_score /
+ * links_score (src/main_link.py:70-171: score every user x item pair, or every unordered pair, keep the
+ * best k) and build_user_sim_matrx + get_add_edge_by_* (:368-453: user x user similarity, per-user
+ * threshold / top share). The n_a x n_b score matrix is never written.
+ *   n2v_row_norms: mean[i] (0 unless centered: pearsonr == cosine of centred rows, :363) and
+ *       inv_norm[i] of emb[rows[i]] (0 for a zero row or rows[i] < 0, so that pair scores 0).
+ *   n2v_sim_threshold: S[r, c] = cos(emb[rows_a[r]], emb[rows_b[c]]) on the fp32 pipes, 64 x 64 tiles;
+ *       a pair is emitted iff S > thr_row[r] (thr_row != NULL) or S > thr, and it passes the masks:
+ *       upper_only = 1 keeps c > r (unordered pairs of one node list, :72), skip_diagonal = 1 scores
+ *       (r, r) as 0 (:386), exclude = sorted int64 keys r * n_b + c (train edges, :73,:84).
+ *       Emitted pairs go to out_a / out_b / out_score (positions into rows_a / rows_b) in no
+ *       particular order; *count (device uint64, zeroed by the caller) counts ALL of them, so a
+ *       caller that sees *count > capacity re-runs with more room or a higher threshold. */
+int n2v_row_norms(const float *emb, int32_t dim, const int32_t *rows, int64_t n, int centered,
+                  float *mean, float *inv_norm, void *stream);
+int n2v_sim_threshold(const float *emb, int32_t dim, const int32_t *rows_a, int32_t n_a,
+                      const int32_t *rows_b, int32_t n_b, const float *mean_a, const float *inv_a,
+                      const float *mean_b, const float *inv_b, const float *thr_row, float thr,
+                      int upper_only, int skip_diagonal, const long long *exclude, int64_t n_exclude,
+                      int32_t *out_a, int32_t *out_b, float *out_score, int64_t capacity,
+                      unsigned long long *count, void *stream);
 
 /* ---- walk-file formatter ---------------------------------------------------------------------
  * replaces: " ".join(map(str, walk)) per line of the walk file (src/main_link.py:237-239,:544-546)

@@ -20,7 +20,7 @@ EXPORTS = [
     "n2v_walk_alias", "n2v_arc_record_bytes", "n2v_pack_arcs", "n2v_walk_alias_packed", "n2v_walk_reject", "n2v_pack_rows", "n2v_edge_hash_capacity", "n2v_edge_hash_build",
     "n2v_walk_reject_indexed", "n2v_walk_reject_law", "n2v_walk_reject_indexed_law", "n2v_vocab_count", "n2v_sgns_prepare_workspace_bytes",
     "n2v_sgns_prepare", "n2v_sgns_init", "n2v_sgns_train", "n2v_sgns_init_part", "n2v_sgns_train_sharded",
-    "n2v_sgns_pairs_workspace_bytes", "n2v_sgns_pairs_count", "n2v_sgns_pairs_fill", "n2v_sgns_train_block", "n2v_cosine_pairs", "n2v_format_workspace_bytes", "n2v_format_walks_offsets", "n2v_format_walks_write", "n2v_parse_workspace_bytes", "n2v_parse_walks_index", "n2v_parse_walks_fill",
+    "n2v_sgns_groups_workspace_bytes", "n2v_sgns_groups_count", "n2v_sgns_groups_fill", "n2v_sgns_train_groups", "n2v_cosine_pairs", "n2v_row_norms", "n2v_sim_threshold", "n2v_format_workspace_bytes", "n2v_format_walks_offsets", "n2v_format_walks_write", "n2v_parse_workspace_bytes", "n2v_parse_walks_index", "n2v_parse_walks_fill",
     "n2v_random_gather_bench",
 ]
 
@@ -59,7 +59,7 @@ def lib():
     L.n2v_last_error.restype = C.c_char_p
     for name in ("n2v_csr_workspace_bytes", "n2v_etab_workspace_bytes", "n2v_sgns_prepare_workspace_bytes",
                  "n2v_arc_record_bytes", "n2v_format_workspace_bytes", "n2v_parse_workspace_bytes",
-                 "n2v_sgns_pairs_workspace_bytes"):
+                 "n2v_sgns_groups_workspace_bytes"):
         getattr(L, name).restype = C.c_size_t
     L.n2v_edge_hash_capacity.restype = C.c_uint64
     _lib = L

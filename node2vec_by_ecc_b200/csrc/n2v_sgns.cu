@@ -97,139 +97,7 @@ __global__ void sgns_init_kernel(float *__restrict__ syn0, float *__restrict__ s
     }
 }
 
-// ---- training -------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-
-// One (centre, context) pair == one fast_sentence_sg_neg call. my_t = this lane's negative draw
-// (lane n holds negative n). Rows: row1 = syn0[context] (input), row2 = syn1neg[target].
-template <int NV, bool ATOMIC>
-__device__ __forceinline__ void apply_target(float4 *row2p, float4 (&row2)[NV], const float4 (&row1)[NV],
-                                             float4 (&work)[NV], float g, const bool (&act)[NV], int lane)
-{
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-        work[c].x += g * row2[c].x; work[c].y += g * row2[c].y;       // work += g * syn1neg[t]
-        work[c].z += g * row2[c].z; work[c].w += g * row2[c].w;
-        if (act[c]) {                                                 // syn1neg[t] += g * row1
-            if (ATOMIC) {
-                atomicAdd(row2p + c * 32 + lane,
-                          make_float4(g * row1[c].x, g * row1[c].y, g * row1[c].z, g * row1[c].w));
-            } else {
-                row2[c].x += g * row1[c].x; row2[c].y += g * row1[c].y;
-                row2[c].z += g * row1[c].z; row2[c].w += g * row1[c].w;
-                row2p[c * 32 + lane] = row2[c];
-            }
-        }
-    }
-}
-
-// Where the rows live. Flat: one [V, dim] table per side on this device. Sharded: row i of a table
-// lives in part i % n_parts (n_parts a power of two; parts may be peer-GPU memory mapped over
-// NVLink) at local row i / n_parts -- vocabulary order is count-descending, so the parts carry
-// equal shares of the traffic.
-struct RowsFlat {
-    float *s0, *s1; int32_t dim;
-    __device__ __forceinline__ float *r0(int32_t i) const { return s0 + (int64_t)i * dim; }
-    __device__ __forceinline__ float *r1(int32_t i) const { return s1 + (int64_t)i * dim; }
-};
-struct RowsSharded {
-    float *const *p0; float *const *p1; int32_t dim, lg, mask;      // p0/p1: 2 x n_parts pointers in shared memory
-    __device__ __forceinline__ float *r0(int32_t i) const { return p0[i & mask] + (int64_t)(i >> lg) * dim; }
-    __device__ __forceinline__ float *r1(int32_t i) const { return p1[i & mask] + (int64_t)(i >> lg) * dim; }
-};
-
-template <int NV, bool ATOMIC, class Rows>
-__device__ __forceinline__ void train_pair(const Rows rows, int32_t dim,
-                                           int32_t centre, int32_t ctx, int32_t my_t, int32_t negative,
-                                           float alpha, const bool (&act)[NV], const float *s_exp, int lane)
-{
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 *row1p = reinterpret_cast<float4 *>(rows.r0(ctx));
-    float4 row1[NV], work[NV];
-#pragma unroll
-    for (int c = 0; c < NV; ++c) { row1[c] = act[c] ? row1p[c * 32 + lane] : zero4; work[c] = zero4; }
-
-    constexpr int FN = 5;   // fast path: gensim's default negative=5, dim <= 128
-    bool fast = (NV == 1) && (negative == FN);
-    int32_t tg[FN + 1];
-    if (fast) {
-        tg[0] = centre;
-#pragma unroll
-        for (int d = 1; d <= FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, my_t, d - 1);
-        // a repeated negative must see the row as updated by its first occurrence: slow path
-#pragma unroll
-        for (int d1 = 1; d1 <= FN; ++d1)
-#pragma unroll
-            for (int d2 = d1 + 1; d2 <= FN; ++d2) if (tg[d1] == tg[d2]) fast = false;
-    }
-    if (fast) {
-        // all target rows in flight at once: one HBM latency per pair instead of six
-        float4 r2[FN + 1][1];
-        float f[FN + 1];
-#pragma unroll
-        for (int d = 0; d <= FN; ++d) {
-            const float4 *rp = reinterpret_cast<const float4 *>(rows.r1(tg[d]));
-            r2[d][0] = (act[0] && !(d > 0 && tg[d] == centre)) ? rp[lane] : zero4;
-        }
-#pragma unroll
-        for (int d = 0; d <= FN; ++d)
-            f[d] = row1[0].x * r2[d][0].x + row1[0].y * r2[d][0].y + row1[0].z * r2[d][0].z + row1[0].w * r2[d][0].w;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int d = 0; d <= FN; ++d) f[d] += __shfl_xor_sync(0xFFFFFFFFu, f[d], o);
-#pragma unroll
-        for (int d = 0; d <= FN; ++d) {
-            if (d > 0 && tg[d] == centre) continue;                               // skipped, not redrawn
-            if (f[d] <= -(float)MAX_EXP || f[d] >= (float)MAX_EXP) continue;
-            const float sg = s_exp[(int)((f[d] + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))];
-            const float g = ((d == 0 ? 1.0f : 0.0f) - sg) * alpha;
-            float4 *row2p = reinterpret_cast<float4 *>(rows.r1(tg[d]));
-            apply_target<1, ATOMIC>(row2p, r2[d], reinterpret_cast<const float4 (&)[1]>(row1),
-                                    reinterpret_cast<float4 (&)[1]>(work), g,
-                                    reinterpret_cast<const bool (&)[1]>(act), lane);
-        }
-    } else {
-        for (int32_t d = 0; d <= negative; ++d) {
-            int32_t target; float label;
-            if (d == 0) { target = centre; label = 1.0f; }
-            else {
-                target = __shfl_sync(0xFFFFFFFFu, my_t, d - 1);
-                if (target == centre) continue;
-                label = 0.0f;
-            }
-            float4 *row2p = reinterpret_cast<float4 *>(rows.r1(target));
-            float4 row2[NV];
-            float f = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NV; ++c) {
-                row2[c] = act[c] ? row2p[c * 32 + lane] : zero4;
-                f += row1[c].x * row2[c].x + row1[c].y * row2[c].y + row1[c].z * row2[c].z + row1[c].w * row2[c].w;
-            }
-            f = warp_sum(f);
-            if (f <= -(float)MAX_EXP || f >= (float)MAX_EXP) continue;
-            const float sg = s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))];
-            const float g = (label - sg) * alpha;
-            apply_target<NV, ATOMIC>(row2p, row2, row1, work, g, act, lane);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < NV; ++c) {
-        if (act[c]) {                                                             // syn0[ctx] += work
-            if (ATOMIC) atomicAdd(row1p + c * 32 + lane, work[c]);
-            else {
-                row1[c].x += work[c].x; row1[c].y += work[c].y;
-                row1[c].z += work[c].z; row1[c].w += work[c].w;
-                row1p[c * 32 + lane] = row1[c];
-            }
-        }
-    }
-}
+// (train_pair / apply_target / RowsFlat / RowsSharded / warp_sum: n2v_sgns_stage.cuh)
 
 // lane n (< negative) draws negative n of pair (i, j)
 __device__ __forceinline__ int32_t draw_pair_negatives(const SgnsArgs &a, const WarpSentence &ws, int32_t i,

@@ -16,6 +16,8 @@ Extra, optional knobs (keyword-only or environment, so existing calls stay valid
 """
 from __future__ import annotations
 
+import gc
+import itertools
 import os
 from collections.abc import Sequence
 
@@ -25,13 +27,82 @@ import torch
 from .graph import AliasTables, DeviceGraph
 
 
+class _RowIter:
+    """iterator of one walk of a WalkCorpus. Nothing is copied from the device until the first
+    __next__; `[map(str, walk) for walk in walks]` (main.py:86) therefore costs one small object per
+    walk, and Word2Vec recognises such sentences (map.__reduce__ exposes this iterator) and trains
+    on the device-resident corpus instead of 80 Python strings per walk."""
+    __slots__ = ("corpus", "index", "_it")
+
+    def __init__(self, corpus, index):
+        self.corpus, self.index, self._it = corpus, index, None
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._it is None:
+            self._it = iter(self.corpus[self.index])
+        return next(self._it)
+
+    @property
+    def untouched(self):
+        return self._it is None
+
+
+class WalkRow(Sequence):
+    """One walk of a WalkCorpus, as iteration over the corpus yields it: behaves like the list of
+    node labels the reference's simulate_walks returns (len, indexing, iteration, == with a list),
+    materialised from the device buffer only when its tokens are actually read."""
+    __slots__ = ("corpus", "index")
+
+    def __init__(self, corpus, index):
+        self.corpus, self.index = corpus, index
+
+    def tolist(self):
+        return self.corpus[self.index]
+
+    def __len__(self):
+        return int(self.corpus._h()[1][self.index])
+
+    def __getitem__(self, k):
+        return self.tolist()[k]
+
+    def __iter__(self):
+        return _RowIter(self.corpus, self.index)
+
+    def __eq__(self, other):
+        if isinstance(other, WalkRow):
+            other = other.tolist()
+        return self.tolist() == other
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return repr(self.tolist())
+
+    def __add__(self, other):
+        return self.tolist() + list(other)
+
+    def __radd__(self, other):
+        return list(other) + self.tolist()
+
+
 class WalkCorpus(Sequence):
     """The list-of-lists simulate_walks returns, kept on the device: int32[n_walks, L] compact
     ids padded with -1. Behaves like a list of lists of ORIGINAL node labels (lazy host copy on
     first Python access); Word2Vec consumes it without leaving the GPU."""
 
-    def __init__(self, walks: torch.Tensor, lens: torch.Tensor, labels):
+    def __init__(self, walks: torch.Tensor, lens: torch.Tensor, labels, shard=None):
         self.walks, self.lens, self.labels = walks, lens, labels
+        # (rank, world, total walks) when this object holds one rank's contiguous share of a corpus that
+        # was simulated by `world` processes (Graph(..., distributed=True)); Word2Vec then trains with
+        # the block-partitioned multi-GPU trainer
+        self.shard = shard
+        self.n_ids = None                 # number of node ids when there are no labels (tokens are compact ids)
         self._host = None
 
     # -- device side
@@ -119,8 +190,48 @@ class WalkCorpus(Sequence):
         return self.labels[row].tolist()
 
     def __iter__(self):
-        for i in range(len(self)):
-            yield self[i]
+        # One small WalkRow per walk. A consumer that keeps them all (`[map(str, walk) for walk in
+        # walks]`, main.py:86) would make CPython's cyclic collector rescan a growing heap of live
+        # objects every few hundred allocations (measured: 4x the loop's own time at 5e5 walks), so
+        # collection is paused while the corpus is being iterated and restored when the loop ends.
+        was = gc.isenabled()
+        gc.disable()
+        try:
+            yield from map(WalkRow, itertools.repeat(self), range(len(self)))
+        finally:
+            if was:
+                gc.enable()
+
+
+def rows_of(sentences):
+    """If `sentences` is a list of walks of ONE WalkCorpus -- WalkRow objects, or untouched
+    map(str, row) / map(<f>, row) iterators over them, in any order -- returns (corpus, row indices,
+    the mapped function or None); otherwise None. Nothing is consumed."""
+    if not isinstance(sentences, (list, tuple)) or not sentences:
+        return None
+    corpus, func, idx = None, None, []
+    for k, sent in enumerate(sentences):
+        f = None
+        if type(sent) is map:
+            try:
+                _, args = sent.__reduce__()
+            except Exception:
+                return None
+            if len(args) != 2:
+                return None
+            f, sent = args
+        if type(sent) is WalkRow:
+            c, i = sent.corpus, sent.index
+        elif type(sent) is _RowIter and sent.untouched:
+            c, i = sent.corpus, sent.index
+        else:
+            return None
+        if k == 0:
+            corpus, func = c, f
+        elif c is not corpus or f is not func:
+            return None
+        idx.append(i)
+    return corpus, idx, func
 
 
 def alias_setup(probs):
@@ -143,6 +254,19 @@ def alias_draw(J, q):
     if np.random.rand() < q[kk]:
         return kk
     return J[kk]
+
+
+class _Identity:
+    """label -> compact id map of a graph whose labels ARE its compact ids"""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __getitem__(self, k):
+        k = int(k)
+        if not 0 <= k < self.n:
+            raise KeyError(k)
+        return k
 
 
 class _TableView:
@@ -177,7 +301,12 @@ class _TableView:
 class Graph:
     """Same constructor and methods as the reference class (node2vec.py:5-237)."""
 
-    def __init__(self, nx_G, is_directed, p, q, popwalk="none", *, seed=None, mode="auto"):
+    def __init__(self, nx_G, is_directed, p, q, popwalk="none", *, seed=None, mode="auto", distributed=None):
+        # distributed (or N2V_DISTRIBUTED=1) with torch.distributed initialised: every process builds the
+        # same graph on its own GPU and simulate_walks returns THIS rank's contiguous share of the walks
+        # (the partitioning main_link.py:263-264 applies across its pool; global walk ids, so the corpus
+        # does not depend on the number of GPUs)
+        self.distributed = (os.environ.get("N2V_DISTRIBUTED", "0") == "1") if distributed is None else bool(distributed)
         self.G = nx_G
         self.is_directed = is_directed
         self.p = p
@@ -218,6 +347,17 @@ class Graph:
     # ---- device graph, rebuilt when the caller swaps/mutates self.G (main_link.py:592) ----------
     @property
     def _dg(self) -> DeviceGraph:
+        if isinstance(self.G, DeviceGraph):
+            # a graph that never existed as a networkx object (100 M edges do not fit one): the CSR built
+            # on the device by DeviceGraph.from_coo is taken as is; node labels are its compact ids
+            if self._dg_obj is not self.G:
+                self._dg_obj, self._dg_for = self.G, None
+                self._tables = self._tables_raw = None
+                self._otf_key = None
+                self._index_map = None
+                if self.G.order is None:
+                    self.G.order = torch.arange(self.G.n, dtype=torch.int32, device=self.G.device)
+            return self._dg_obj
         key = (id(self.G), self.G.number_of_nodes(), self.G.number_of_edges())
         if self._dg_obj is None or self._dg_for != key:
             self._dg_obj = DeviceGraph.from_networkx(self.G)
@@ -230,6 +370,8 @@ class Graph:
     @property
     def _index(self):
         self._dg
+        if self._index_map is None:                     # DeviceGraph without labels: ids are the labels
+            return _Identity(self._dg.n)
         return self._index_map
 
     def _table_budget(self) -> int:
@@ -289,7 +431,16 @@ class Graph:
 
     def _starts(self, num_walks, nodes):
         dg = self._dg
-        if not nodes:                                   # `if not nodes` (node2vec.py:87)
+        if isinstance(nodes, (torch.Tensor, np.ndarray)):   # compact ids / integer labels in bulk
+            ids = torch.as_tensor(nodes)
+            if dg.labels is not None:
+                lab = torch.as_tensor(np.asarray(dg.labels, dtype=np.int64))
+                pos = torch.searchsorted(lab, ids.to(torch.int64).cpu())
+                if bool((pos >= lab.numel()).any()) or not torch.equal(lab[pos.clamp_max(lab.numel() - 1)], ids.to(torch.int64).cpu()):
+                    raise KeyError("start node not in the graph")
+                ids = pos
+            order = ids.to(device=dg.device, dtype=torch.int32, non_blocking=True)
+        elif not nodes:                                 # `if not nodes` (node2vec.py:87)
             order = dg.order
         else:
             idx = self._index
@@ -305,6 +456,14 @@ class Graph:
                 print(str(it + 1), '/', str(num_walks))
         base = self._walk_id_base
         self._walk_id_base += int(starts.shape[0])
+        shard = None
+        if self.distributed:
+            from . import dist as D
+            rank, world = D.world()
+            if world > 1:
+                total = int(starts.shape[0])
+                lo, hi = D.shard_range(total, rank, world)
+                starts, base, shard = starts[lo:hi].contiguous(), base + lo, (rank, world, total)
         if tables.edge_slots is not None:
             walks, lens = dg.walk_alias(tables, starts, int(walk_length), self.seed, base)
         else:
@@ -318,7 +477,9 @@ class Graph:
                 plain = tables if not tables.popwalk else dg.plain_node_tables()
             walks, lens = dg.walk_reject(float(self.p), float(self.q), starts, int(walk_length), self.seed,
                                          base, node_tables=plain, first_tables=first, pop_edges=pop_edges)
-        return WalkCorpus(walks, lens, dg.labels)
+        corpus = WalkCorpus(walks, lens, dg.labels, shard)
+        corpus.n_ids = dg.n
+        return corpus
 
     def simulate_walks(self, num_walks, walk_length, nodes=None, verbose=False):
         """node2vec.py:81-95."""

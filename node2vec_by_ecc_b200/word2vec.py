@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from ._lib import N2VError, SgnsParams, check, lib, ptr, require_cuda, stream
-from .walker import WalkCorpus
+from .walker import WalkCorpus, rows_of
 
 
 class Vocab:
@@ -64,8 +64,20 @@ class KeyedVectors:
         self.vocab = {}
         self.index2word = []
         self.vector_size = vector_size
-        self._syn0_dev = None
+        self._syn0_dev_ = None
         self._syn0_host = None
+        self._gather = None               # multi-GPU: () -> full device table, called when the rows are first read
+
+    @property
+    def _syn0_dev(self):
+        if self._syn0_dev_ is None and self._gather is not None:
+            self._syn0_dev_ = self._gather()
+            self._gather = None
+        return self._syn0_dev_
+
+    @_syn0_dev.setter
+    def _syn0_dev(self, t):
+        self._syn0_dev_, self._gather = t, None
 
     @property
     def syn0(self):
@@ -116,56 +128,15 @@ class KeyedVectors:
                                      ptr(out), stream()))
         return out.cpu().numpy()
 
-    def top_k_links(self, words_a, words_b=None, k=10, exclude=(), block_rows=4096):
+    def top_k_links(self, words_a, words_b=None, k=10, exclude=(), block_rows=None):
         """All-pairs link scoring of link_prediction / make_links_and_score / links_score
         (main_link.py:69-171): cosine of every candidate pair -- words_a x words_b ("separated"
         user x item mode) or, with words_b None, every unordered pair i < j of words_a -- minus the
         `exclude` pairs (train edges, either orientation), global top-k by score.
-        -> list of ((a, b), score), best first. One [block, d] x [d, |B|] cuBLAS SGEMM per block of
-        rows (the one dense-GEMM spot of the path) + a running top-k on the device."""
-        dev = require_cuda()
-        words_a = list(words_a)
-        same = words_b is None
-        words_b = words_a if same else list(words_b)
-        emb = (self._syn0_dev if self._syn0_dev is not None else torch.as_tensor(self._syn0_host).to(dev)).float()
-        emb = emb / emb.norm(dim=1, keepdim=True).clamp_min(1e-30)
-        ia = torch.as_tensor([self.vocab[w].index for w in words_a], device=dev)
-        ib = torch.as_tensor([self.vocab[w].index for w in words_b], device=dev)
-        A, Bm = emb[ia], emb[ib]
-        pos_a = {w: i for i, w in enumerate(words_a)}
-        pos_b = pos_a if same else {w: i for i, w in enumerate(words_b)}
-        ex = []
-        for a, b in exclude:
-            if a in pos_a and b in pos_b:
-                ex.append((pos_a[a], pos_b[b]))
-            if b in pos_a and a in pos_b:
-                ex.append((pos_a[b], pos_b[a]))
-        ex = torch.as_tensor(ex, dtype=torch.int64, device=dev).reshape(-1, 2)
-        best_s = torch.full((0,), 0.0, device=dev)
-        best_i = torch.zeros((0,), dtype=torch.int64, device=dev)
-        nb = len(words_b)
-        for r0 in range(0, len(words_a), block_rows):
-            r1 = min(len(words_a), r0 + block_rows)
-            S = A[r0:r1] @ Bm.T
-            if same:                                   # pairs i < j only (main_link.py:72)
-                rows = torch.arange(r0, r1, device=dev)[:, None]
-                S.masked_fill_(torch.arange(nb, device=dev)[None, :] <= rows, float("-inf"))
-            if ex.numel():
-                m = (ex[:, 0] >= r0) & (ex[:, 0] < r1)
-                S[ex[m, 0] - r0, ex[m, 1]] = float("-inf")
-            kk = min(k, S.numel())
-            s, i = torch.topk(S.reshape(-1), kk)
-            best_s = torch.cat([best_s, s]); best_i = torch.cat([best_i, i + r0 * nb])
-            if best_s.numel() > k:
-                s, o = torch.topk(best_s, k)
-                best_s, best_i = s, best_i[o]
-        keep = torch.isfinite(best_s)
-        best_s, best_i = best_s[keep], best_i[keep]
-        order = torch.argsort(best_s, descending=True, stable=True)
-        out = []
-        for s, i in zip(best_s[order].tolist(), best_i[order].tolist()):
-            out.append(((words_a[i // nb], words_b[i % nb]), s))
-        return out
+        -> list of ((a, b), score), best first. Tiles of the score matrix are computed and selected
+        in one kernel (n2v_sim_threshold); the matrix itself is never written (scoring.top_k_links)."""
+        from .scoring import top_k_links
+        return top_k_links(self, words_a, words_b, k, exclude)
 
     def most_similar(self, positive, topn=10):
         if isinstance(positive, (str, bytes)):
@@ -244,9 +215,11 @@ class SgnsTrainer:
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
               epoch=0, sent_per_job=125, grid_warps=None, atomic_updates=1, alpha=None, min_alpha=None,
-              tuning=None, negative_sharing=0):
+              tuning=None, negative_sharing=0, vocab_of_id=None):
         """One pass over n_sent sentences (asynchronous on the current stream); self.pairs
-        (device int64) accumulates the (centre, context) pairs trained."""
+        (device int64) accumulates the (centre, context) pairs trained. vocab_of_id: token id ->
+        vocabulary row (-1 = not in the vocabulary) when the tokens are not in the id space the
+        trainer was built over."""
         P = SgnsParams()
         P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
         P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
@@ -260,7 +233,7 @@ class SgnsTrainer:
         P.negative_sharing = int(negative_sharing)
         P.tuning = int(os.environ.get("N2V_SGNS_TUNING", "0")) if tuning is None else int(tuning)
         check(lib().n2v_sgns_train(ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride),
-                                   C.c_int64(sent_id_base), ptr(self.vocab_of_id),
+                                   C.c_int64(sent_id_base), ptr(self.vocab_of_id if vocab_of_id is None else vocab_of_id),
                                    ptr(self.keep_thr if self.sample > 0 else None), ptr(self.cum_table),
                                    ptr(self.bucket_lo), C.byref(P), ptr(self.syn0), ptr(self.syn1neg),
                                    ptr(self.pairs), stream()))
@@ -367,18 +340,23 @@ class BlockSgnsTrainer(SgnsTrainer):
         1's, ... (all-gathered, 4 bytes per token), sentence ids sent_id_base + position in pool;
       * single process, local_parts = n: all parts on this device, buckets run in the order the n
         GPUs would run them (the exact emulation the parity and AUC tests use; n = 1 is a plain
-        single-GPU trainer over a pair stream).
-    alpha is fixed per pool: alpha0 - (alpha0 - min_alpha) * example_base / total_examples."""
+        single-GPU trainer over a group stream).
+    The law is SgnsTrainer's shared-negative law whatever n_parts is: one negative set per centre
+    occurrence -- the same Philox draws, mapped into the centre's part -- and the sentence's job alpha
+    (example_base / total_examples / sent_per_job as in SgnsTrainer.train). neg_group = G > 1 shares
+    a set among the centres at G consecutive positions of a walk (faster at many parts, a different
+    estimator: scripts/auc_block.py)."""
 
-    def __init__(self, counts_by_id, *args, local_parts: int = 0, run_pairs: int = 32, **kw):
+    def __init__(self, counts_by_id, *args, local_parts: int = 0, neg_group: int = 1, **kw):
         from . import dist as D
         self._rank, self._world = D.world()
         self._local_parts = int(local_parts)
         self.n_parts = self._local_parts if self._local_parts else self._world
         if self.n_parts not in (1, 2, 4, 8):
             raise ValueError("the tables can be cut into 1, 2, 4 or 8 parts")
-        self.run_pairs = int(run_pairs)
-        self._pool = 0
+        self.neg_group = int(neg_group)
+        if not 1 <= self.neg_group <= 256:
+            raise ValueError("neg_group must be in [1, 256]")
         self._buf = {}
         self.phase_events = None          # set to [] to record (phase, start event, end event) per train()
         super().__init__(counts_by_id, *args, **kw)
@@ -386,6 +364,8 @@ class BlockSgnsTrainer(SgnsTrainer):
             raise ValueError("fewer vocabulary rows than parts")
         if self.dim % 4 or self.dim > 128:
             raise ValueError("block-partitioned tables need dim to be a multiple of 4, <= 128")
+        if self.negative != 5:
+            raise ValueError("block-partitioned tables run the shared-negative law with negative = 5")
 
     @property
     def _mine(self):
@@ -408,56 +388,72 @@ class BlockSgnsTrainer(SgnsTrainer):
         sms = int(lib().n2v_sm_count())
         return int(max(4, min(sms * 20, (self.V // self.n_parts) // 4)))
 
-    def pool_alpha(self, example_base: int, total_examples: int, alpha=None, min_alpha=None) -> float:
-        a0 = self.alpha if alpha is None else float(alpha)
-        m = self.min_alpha if min_alpha is None else float(min_alpha)
-        return float(np.float32(max(m, a0 - (a0 - m) * (float(example_base) / float(max(1, total_examples))))))
-
-    def _params(self, epoch, grid_warps):
+    def _params(self, epoch, grid_warps, *, total_examples=1, example_base=0, sent_per_job=1, alpha=None,
+                min_alpha=None):
         P = SgnsParams()
         P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
         P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
-        P.alpha0, P.min_alpha, P.total_examples, P.example_base, P.sent_per_job = self.alpha, self.min_alpha, 1, 0, 1
+        P.alpha0 = self.alpha if alpha is None else float(alpha)
+        P.min_alpha = self.min_alpha if min_alpha is None else float(min_alpha)
+        P.total_examples, P.example_base = int(total_examples), int(example_base)
+        P.sent_per_job = max(1, int(sent_per_job))
         P.epoch, P.seed = int(epoch), self.seed
         P.grid_warps = int(grid_warps or self.default_hogwild_warps())
-        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, int(os.environ.get("N2V_BLK_TUNING", "0"))
+        P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
         return P
 
-    def make_pairs(self, tokens, sent_off, n_sent, stride, sent_id_base, P, part):
-        """-> (pairs int32[total, 2], bounds): stream b of `part` = pairs[bounds[b]:bounds[b + 1]]"""
+    def make_groups(self, tokens, sent_off, n_sent, stride, sent_id_base, P, part, exact_bounds=True):
+        """-> (words uint32[capacity], bounds | None): stream b of `part` = words[bounds[b]:bounds[b + 1]].
+        exact_bounds=False skips the host read of the stream bounds when the buffer already has 1.5x
+        the room the previous pool needed (the kernels then read the bounds on the device and clamp to
+        the capacity; check_overflow() tells whether a pool ever did not fit)."""
         dev, W = self.counts.device, self.n_parts
         b = self._buf.setdefault(part, {})
         n_off = W * n_sent + 1
         if b.get("n_off", 0) < n_off:
             b["offsets"] = torch.empty(n_off, dtype=torch.int64, device=dev)
-            b["ws"] = torch.empty(int(lib().n2v_sgns_pairs_workspace_bytes(C.c_int64(n_sent), C.c_int32(W))),
+            b["ws"] = torch.empty(int(lib().n2v_sgns_groups_workspace_bytes(C.c_int64(n_sent), C.c_int32(W))),
                                   dtype=torch.uint8, device=dev)
             b["n_off"] = n_off
             b["overflow"] = torch.zeros(1, dtype=torch.int64, device=dev)
+            b["need"] = None
         keep = ptr(self.keep_thr if self.sample > 0 else None)
         head = (ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride), C.c_int64(sent_id_base),
                 ptr(self.vocab_of_id), keep, C.byref(P), C.c_int32(part), C.c_int32(W))
-        check(lib().n2v_sgns_pairs_count(*head, ptr(b["offsets"]), ptr(b["ws"]), C.c_size_t(b["ws"].numel()), stream()))
-        bounds = [int(x) for x in b["offsets"][: n_off : n_sent].cpu().tolist()]     # one small D2H read per pool
-        total = bounds[-1]
-        if b.get("cap", -1) < total:
-            b["cap"] = int(total * 1.1) + 1024
-            b["pairs"] = torch.empty((b["cap"], 2), dtype=torch.int32, device=dev)
-        check(lib().n2v_sgns_pairs_fill(*head, ptr(b["offsets"]), ptr(b["pairs"]), C.c_int64(b["cap"]),
-                                        ptr(b["overflow"]), stream()))
-        return b["pairs"], bounds
+        check(lib().n2v_sgns_groups_count(*head, ptr(b["offsets"]), ptr(b["ws"]), C.c_size_t(b["ws"].numel()), stream()))
+        bounds = None
+        lazy = (not exact_bounds and b.get("need") is not None and b.get("need_n") == n_sent
+                and b.get("cap", -1) >= int(b["need"] * 1.5))
+        if not lazy:
+            bounds = [int(x) for x in b["offsets"][: n_off : n_sent].cpu().tolist()]     # one small D2H read
+            total = bounds[-1]
+            b["need"], b["need_n"] = total, n_sent
+            want = int(total * (1.1 if exact_bounds else 1.6)) + 1024
+            if b.get("cap", -1) < (total if exact_bounds else int(total * 1.5)):
+                b["cap"] = want
+                b["words"] = torch.empty(want, dtype=torch.int32, device=dev)
+        check(lib().n2v_sgns_groups_fill(*head, ptr(b["offsets"]), ptr(b["words"]), C.c_int64(b["cap"]),
+                                         ptr(b["overflow"]), stream()))
+        return b["words"], bounds
 
-    def train_bucket(self, pairs, first, n, syn0_part, part, bucket, P, alpha):
-        if n <= 0:
-            return
-        tag = (self._pool * 64 + part * 8 + bucket) & 0xFFFFFFFF
-        check(lib().n2v_sgns_train_block(C.c_void_p(pairs.data_ptr() + 8 * first), C.c_int64(n), ptr(self.cum_table),
-                                         ptr(self.bucket_lo), C.byref(P), C.c_float(alpha), C.c_int32(self.run_pairs),
-                                         C.c_uint32(tag), ptr(syn0_part), ptr(self.parts1[part]), C.c_int32(part),
-                                         C.c_int32(self.n_parts), ptr(self.pairs), stream()))
+    def train_bucket(self, part, bucket, syn0_part, P, n_sent, sent_id_base, bounds=None):
+        b = self._buf[part]
+        if bounds is not None:
+            first, n = bounds[bucket], bounds[bucket + 1] - bounds[bucket]
+            if n <= 0:
+                return
+            d0 = d1 = C.c_void_p(0)
+        else:                      # bounds stay on the device: two entries of the offsets array
+            first, n = 0, 0
+            base = b["offsets"].data_ptr()
+            d0, d1 = C.c_void_p(base + 8 * bucket * n_sent), C.c_void_p(base + 8 * (bucket + 1) * n_sent)
+        check(lib().n2v_sgns_train_groups(ptr(b["words"]), C.c_int64(first), C.c_int64(n), d0, d1, C.c_int64(b["cap"]),
+                                          C.c_int64(sent_id_base), ptr(self.cum_table), ptr(self.bucket_lo), C.byref(P),
+                                          C.c_int32(self.neg_group), ptr(syn0_part), ptr(self.parts1[part]),
+                                          C.c_int32(part), C.c_int32(self.n_parts), ptr(self.pairs), stream()))
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
-              epoch=0, grid_warps=None, alpha=None, min_alpha=None, **_ignored):
+              epoch=0, sent_per_job=125, grid_warps=None, alpha=None, min_alpha=None, exact_bounds=True, **_ignored):
         """One pool. Multi-GPU: every rank passes its own walks (fixed-stride buffer, same n_sent on
         every rank) and the POOL's example_base / sent_id_base (identical on all ranks)."""
         from . import dist as D
@@ -473,24 +469,23 @@ class BlockSgnsTrainer(SgnsTrainer):
         if n_sent <= 0:
             return
         t = mark("gather", t)
-        P = self._params(epoch, grid_warps)
-        al = self.pool_alpha(example_base, total_examples, alpha, min_alpha)
-        streams = {k: self.make_pairs(tokens, sent_off, n_sent, stride, sent_id_base, P, k) for k in self._mine}
+        P = self._params(epoch, grid_warps, total_examples=total_examples, example_base=example_base,
+                         sent_per_job=sent_per_job, alpha=alpha, min_alpha=min_alpha)
+        streams = {k: self.make_groups(tokens, sent_off, n_sent, stride, sent_id_base, P, k, exact_bounds)
+                   for k in self._mine}
         t = mark("pairs", t)
         held = None if self._local_parts else self.parts0[self._rank]
         for e in range(W):
             for k in self._mine:
                 b = (k + e) % W
-                pairs, bounds = streams[k]
-                self.train_bucket(pairs, bounds[b], bounds[b + 1] - bounds[b],
-                                  self.parts0[b] if self._local_parts else held, k, b, P, al)
+                self.train_bucket(k, b, self.parts0[b] if self._local_parts else held, P, n_sent, sent_id_base,
+                                  streams[k][1])
             t = mark("train", t)
             if multi:                                    # the syn0 part moves on; after W passes it is home again
                 held, self._spare = D.ring_pass(held, self._spare)
                 t = mark("ring", t)
         if multi:
             self.parts0[self._rank] = held
-        self._pool += 1
 
     def _mark(self, phase=None, since=None):
         if self.phase_events is None:
@@ -504,7 +499,7 @@ class BlockSgnsTrainer(SgnsTrainer):
     def check_overflow(self):
         for b in self._buf.values():
             if int(b["overflow"].item()):
-                raise N2VError("pair buffer overflow (internal sizing error)")
+                raise N2VError("group buffer overflow: a pool did not fit the stream buffer")
 
     def gather(self):
         """-> (syn0, syn1neg) float32[V, dim] on this device, rows in vocabulary order"""
@@ -555,7 +550,7 @@ class Word2Vec:
         self.wv = KeyedVectors(self.vector_size)
         self.corpus_count = 0
         self.train_count = 0
-        self.pairs_trained = 0
+        self._pairs_done, self._pairs_pending, self._shard = 0, None, None
         self.syn1neg = None
         if sentences is not None:
             self.build_vocab(sentences)
@@ -576,10 +571,36 @@ class Word2Vec:
         """-> (tokens int32 device [n_tok] or [n_sent, stride], sent_off device|None, stride,
         n_sent, words list indexed by token id)"""
         dev = require_cuda()
+        func = str
+        self._shard = None
+        if not isinstance(sentences, WalkCorpus):
+            # `[map(str, walk) for walk in walks]` (main.py:86) over a WalkCorpus: the rows are lazy, the map
+            # objects expose them (walker.rows_of) -- train on the device corpus, no Python strings at all
+            r = rows_of(sentences)
+            if r is not None and (r[2] is None or r[2] is str):
+                corpus, idx, func = r
+                if idx == list(range(len(corpus))):
+                    sentences = corpus
+                else:
+                    sel = torch.as_tensor(idx, dtype=torch.int64, device=corpus.walks.device)
+                    sentences = WalkCorpus(corpus.walks[sel].contiguous(), corpus.lens[sel].contiguous(), corpus.labels,
+                                           corpus.shard)
+                    sentences.n_ids = corpus.n_ids
         if isinstance(sentences, WalkCorpus):     # already on the device: tokens are compact node ids
+            self._shard = sentences.shard
             labels = sentences.labels
-            n_ids = int(len(labels)) if labels is not None else int(sentences.walks.max().item()) + 1
-            words = [str(l) for l in (labels.tolist() if labels is not None else range(n_ids))]
+            key = (id(labels), func) if labels is not None else None
+            if key is not None and getattr(self, "_words_key", None) == key:
+                words = self._words_cache           # same graph as last time: the label list is reused
+            else:
+                n_ids = int(len(labels)) if labels is not None else (
+                    int(sentences.n_ids) if getattr(sentences, "n_ids", None) else int(sentences.walks.max().item()) + 1)
+                key = ("ids", n_ids, func) if labels is None else key
+                if getattr(self, "_words_key", None) == key:
+                    return sentences.walks, None, int(sentences.walks.shape[1]), int(sentences.walks.shape[0]), self._words_cache
+                src = labels.tolist() if labels is not None else range(n_ids)
+                words = [str(l) for l in src] if func is str else list(src)
+                self._words_key, self._words_cache, self._words_labels = key, words, labels
             return sentences.walks, None, int(sentences.walks.shape[1]), int(sentences.walks.shape[0]), words
         if isinstance(sentences, LineSentence) and isinstance(sentences.source, (str, os.PathLike)) \
                 and sentences.limit is None:
@@ -650,14 +671,29 @@ class Word2Vec:
         dev = require_cuda()
         tok, off, stride, n_sent, words = self._ingest(sentences)
         self._corpus = (tok, off, stride, n_sent)
+        self._vocab_words = words                 # token id -> word of the corpus the vocabulary was built from
         self.corpus_count = n_sent
         n_ids = len(words)
         counts = torch.zeros(max(n_ids, 1), dtype=torch.int64, device=dev)
         check(lib().n2v_vocab_count(ptr(tok), C.c_int64(tok.numel()), C.c_int32(n_ids), ptr(counts), stream()))
-        self.trainer = T = SgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
-                                       negative=self.negative, sample=self.sample, seed=self.seed,
-                                       alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
-                                       batch_words=self.batch_words)
+        shard = getattr(self, "_shard", None)
+        if shard is not None:
+            # one rank's share of a corpus simulated by `world` processes: global counts, tables cut into
+            # `world` row sets, block-partitioned training over an NCCL ring (BlockSgnsTrainer)
+            from . import dist as D
+            if off is not None or self.vector_size > 128 or self.vector_size % 4 or self.negative != 5:
+                raise NotImplementedError("multi-GPU training needs a walk corpus, size <= 128 (multiple of 4), negative = 5")
+            D.sum_counts(counts)
+            self.corpus_count = int(shard[2])
+            self.trainer = T = BlockSgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
+                                                negative=self.negative, sample=self.sample, seed=self.seed,
+                                                alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
+                                                batch_words=self.batch_words)
+        else:
+            self.trainer = T = SgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
+                                           negative=self.negative, sample=self.sample, seed=self.seed,
+                                           alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
+                                           batch_words=self.batch_words)
         # host-side vocabulary objects (what emb.vocab / index2word expose)
         order_h, vc_h = T.order.cpu().numpy(), T.counts.cpu().numpy()
         kt_h = T.keep_thr.cpu().numpy().view(np.uint32)
@@ -665,6 +701,32 @@ class Word2Vec:
         self.wv.vocab = {w: Vocab(i, int(vc_h[i]), int(kt_h[i])) for i, w in enumerate(self.wv.index2word)}
         self.wv.vector_size = self.vector_size
         self.wv._syn0_dev, self.wv._syn0_host = T.syn0, None
+
+    def _train_sharded(self, tok, n_sent, stride, epochs, start_alpha, end_alpha):
+        """every rank's share of the corpus, pool by pool (pool = the same slice of every rank's share;
+        shares are padded with empty walks to one length so that all ranks run the same pools)"""
+        T = self.trainer
+        rank, world, total = self._shard
+        per = -(-total // world)
+        if n_sent < per:
+            tok = torch.cat([tok, torch.full((per - n_sent, stride), -1, dtype=tok.dtype, device=tok.device)])
+        pool = int(min(per, max(1024, int(os.environ.get("N2V_POOL_WALKS", str(1 << 19))))))
+        mean_len = max(1.0, T.raw_words / max(self.corpus_count, 1))
+        before = T.pairs[0].clone()
+        for ep in range(epochs):
+            for p0 in range(0, per, pool):
+                n = min(pool, per - p0)
+                T.train(tok[p0:p0 + n].contiguous(), None, n, stride, total_examples=max(1, per * world * epochs),
+                        example_base=(ep * per + p0) * world, sent_id_base=(ep * per + p0) * world, epoch=ep,
+                        sent_per_job=int(self.batch_words // mean_len), grid_warps=self.hogwild_warps,
+                        alpha=start_alpha, min_alpha=end_alpha)
+        T.check_overflow()
+        import torch.distributed as tdist
+        mine = T.pairs[0] - before
+        tdist.all_reduce(mine)
+        self._pairs_pending = mine if self._pairs_pending is None else self._pairs_pending + mine
+        self.wv._syn0_dev, self.wv._syn0_host = None, None        # all-gathered when the table is first read
+        self.wv._gather = lambda: T.gather()[0]
 
     # test/inspection handles
     @property
@@ -694,20 +756,42 @@ class Word2Vec:
     # ---- training ------------------------------------------------------------------------------
     def train(self, sentences=None, total_examples=None, total_words=None, epochs=None,
               start_alpha=None, end_alpha=None, **_):
+        vmap = None
         if sentences is None or isinstance(sentences, tuple):
             tok, off, stride, n_sent = self._corpus if sentences is None else sentences
         else:
-            raise NotImplementedError("train() on a new corpus: rebuild the model with that corpus")
+            # gensim's model.train(new_sentences, total_examples=, epochs=) on the existing vocabulary:
+            # words the vocabulary does not hold are ignored, as gensim ignores them
+            if getattr(self, "trainer", None) is None:
+                raise RuntimeError("you must first build vocabulary before training the model")
+            tok, off, stride, n_sent, words = self._ingest(sentences)
+            if words is not self._vocab_words:
+                v = self.wv.vocab
+                vmap = torch.as_tensor(np.fromiter((v[w].index if w in v else -1 for w in words), dtype=np.int32,
+                                                   count=len(words))).to(tok.device)
         T = self.trainer
         epochs = self.iter if epochs is None else int(epochs)
-        mean_len = max(1.0, T.raw_words / max(n_sent, 1))
-        before = int(T.pairs[0].item())
-        for ep in range(epochs):
-            T.train(tok, off, n_sent, stride, total_examples=int(n_sent) * epochs, example_base=ep * int(n_sent),
-                    epoch=ep, sent_per_job=int(self.batch_words // mean_len), grid_warps=self.hogwild_warps,
-                    atomic_updates=self.atomic_updates, alpha=start_alpha, min_alpha=end_alpha,
-                    negative_sharing=self.shared_negatives if (self.vector_size <= 128 and self.negative == 5) else 0)
-        self.pairs_trained += int(T.pairs[0].item()) - before
+        if getattr(self, "_shard", None) is not None:
+            self.train_count += 1
+            return self._train_sharded(tok, n_sent, stride, epochs, start_alpha, end_alpha)
+        n_ex = int(n_sent) if total_examples is None else int(total_examples)
+        mean_len = max(1.0, T.raw_words / max(self.corpus_count, 1))
         self.train_count += 1
+        before = T.pairs[0].clone()
+        for ep in range(epochs):
+            T.train(tok, off, n_sent, stride, total_examples=max(1, n_ex * epochs), example_base=ep * n_ex,
+                    epoch=ep + 1000 * (self.train_count - 1), sent_per_job=int(self.batch_words // mean_len),
+                    grid_warps=self.hogwild_warps, atomic_updates=self.atomic_updates, alpha=start_alpha,
+                    min_alpha=end_alpha, vocab_of_id=vmap,
+                    negative_sharing=self.shared_negatives if (self.vector_size <= 128 and self.negative == 5) else 0)
+        self._pairs_pending = (T.pairs[0] - before) if getattr(self, "_pairs_pending", None) is None \
+            else self._pairs_pending + (T.pairs[0] - before)
         self.wv._syn0_dev, self.wv._syn0_host = T.syn0, None
-        return self.pairs_trained
+
+    @property
+    def pairs_trained(self):
+        """(centre, context) pairs trained so far; reading it waits for the device"""
+        if getattr(self, "_pairs_pending", None) is not None:
+            self._pairs_done += int(self._pairs_pending.item())
+            self._pairs_pending = None
+        return self._pairs_done

@@ -384,21 +384,24 @@ int sgns_oracle_train(const int32_t *tok, const int64_t *sent_off, int64_t n_sen
  * Not gensim's schedule: the multi-GPU form of the same per-pair arithmetic. Tables cut into
  * n_parts = 1 << lg row sets (row i -> part i % n_parts, local row i / n_parts).
  *
- * sgns_oracle_make_pairs: the (centre, context) pairs of the sentences whose centre lies in `part`,
+ * sgns_oracle_make_groups: the (centre, context) pairs of the sentences whose centre lies in `part`,
  * sub-sampling and window shrink addressed by Philox exactly as rng_mode bit 0 above, written as
- * n_parts streams (stream b = context in part b) in the order sentence, centre, context. Two
- * calls: pairs == NULL counts (stream_len[b]), then fill with stream_off[b] = start of stream b. */
-int sgns_oracle_make_pairs(const int32_t *tok, const int64_t *sent_off, int64_t n_sent, int64_t sent_id_base,
-                           int32_t window, const uint64_t *sample_int, uint64_t seed, uint32_t epoch,
-                           int32_t part, int32_t lg, int64_t *stream_len, const int64_t *stream_off,
-                           int32_t *pairs)
+ * n_parts streams (stream b = context in part b) in the order sentence, centre, context. The pairs
+ * of one centre occurrence inside a stream form a group: {0x80000000 | centre local row, sentence
+ * index, position | pairs << 16}, then one word per pair (context local row). Two calls: words ==
+ * NULL counts (stream_len[b], in words), then fill with stream_off[b] = start of stream b. */
+int sgns_oracle_make_groups(const int32_t *tok, const int64_t *sent_off, int64_t n_sent, int64_t sent_id_base,
+                            int32_t window, const uint64_t *sample_int, uint64_t seed, uint32_t epoch,
+                            int32_t part, int32_t lg, int64_t *stream_len, const int64_t *stream_off,
+                            uint32_t *words)
 {
     const int32_t n_parts = 1 << lg, mask = n_parts - 1;
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
     int32_t *red = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
-    int64_t cur[64];
-    if (!idx || !red) { free(idx); free(red); return -1; }
-    for (int32_t b = 0; b < n_parts; ++b) cur[b] = pairs ? stream_off[b] : 0;
+    int32_t *pos = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
+    int64_t cur[64], hdr[64]; int32_t cnt[64];
+    if (!idx || !red || !pos) { free(idx); free(red); free(pos); return -1; }
+    for (int32_t b = 0; b < n_parts; ++b) cur[b] = words ? stream_off[b] : 0;
     for (int64_t s = 0; s < n_sent; ++s) {
         const uint64_t gs = (uint64_t)(sent_id_base + s);
         const int64_t b0 = sent_off[s], e0 = sent_off[s + 1];
@@ -408,102 +411,95 @@ int sgns_oracle_make_pairs(const int32_t *tok, const int64_t *sent_off, int64_t 
             if (w < 0) continue;
             uint32_t r[4]; philox_words(seed, gs, (uint32_t)(t - b0), epoch << 8, r);
             if (sample_int && sample_int[w] < (uint64_t)r[0]) continue;
-            idx[n] = w; red[n] = (int32_t)(r[1] % (uint32_t)window); ++n;
+            idx[n] = w; red[n] = (int32_t)(r[1] % (uint32_t)window); pos[n] = (int32_t)(t - b0); ++n;
         }
         for (int64_t i = 0; i < n; ++i) {
             if ((idx[i] & mask) != part) continue;
             int64_t j = i - window + red[i]; if (j < 0) j = 0;
             int64_t k = i + window + 1 - red[i]; if (k > n) k = n;
+            for (int32_t b = 0; b < n_parts; ++b) { hdr[b] = -1; cnt[b] = 0; }
             for (; j < k; ++j) {
                 if (j == i) continue;
                 const int32_t b = idx[j] & mask;
-                if (pairs) { pairs[2 * cur[b]] = idx[i] >> lg; pairs[2 * cur[b] + 1] = idx[j] >> lg; }
-                ++cur[b];
+                if (hdr[b] < 0) { hdr[b] = cur[b]; cur[b] += 3; }
+                if (words) words[cur[b]] = (uint32_t)(idx[j] >> lg);
+                ++cur[b]; ++cnt[b];
             }
+            if (words)
+                for (int32_t b = 0; b < n_parts; ++b)
+                    if (hdr[b] >= 0) {
+                        words[hdr[b]] = 0x80000000u | (uint32_t)(idx[i] >> lg);
+                        words[hdr[b] + 1] = (uint32_t)s;
+                        words[hdr[b] + 2] = (uint32_t)pos[i] | ((uint32_t)cnt[b] << 16);
+                    }
         }
     }
-    if (!pairs) for (int32_t b = 0; b < n_parts; ++b) stream_len[b] = cur[b];
-    free(idx); free(red);
+    if (!words) for (int32_t b = 0; b < n_parts; ++b) stream_len[b] = cur[b];
+    free(idx); free(red); free(pos);
     return 0;
 }
 
-/* sgns_oracle_block_train: one stream against (syn0 part, syn1neg part `part`). One negative set
- * per run of K consecutive pairs: Philox ctr (run lo, run hi, tag, epoch << 8 | 1 + n / 4), draw
- * mapped to the word of the same local row in `part`; a row repeated in the set is used once; the
- * centre row and the set are worked on in private copies for the run and written back as
- * (copy - first read), which is what the device's carried registers + reductions do. */
-int sgns_oracle_block_train(const int32_t *pairs, int64_t n_pairs, float *syn0_part, float *syn1_part,
-                            int32_t part, int32_t lg, int32_t V, int32_t dim, const uint32_t *cum_table,
-                            float alpha, int32_t K, uint64_t seed, uint32_t epoch, uint32_t tag)
+/* sgns_oracle_train_groups: one stream against (syn0 part, syn1neg part `part`), group by group in
+ * stream order. The law is rng_mode 3 above (Philox + one negative set per centre occurrence) with
+ * every draw mapped to the word of the same local row in `part`: ctr = (sentence id, position / G <<
+ * 16 | 0xFFFF, epoch << 8 | 1 + n / 4); alpha = the sentence's job alpha (jobs of sent_per_job
+ * sentences, as the device's job_alpha). Pairs run through fast_sentence_sg_neg's arithmetic in
+ * order, updates immediate -- which is what the device's carried registers + one reduction per row
+ * compute when one warp runs alone. */
+int sgns_oracle_train_groups(const uint32_t *words, int64_t n_words, float *syn0_part, float *syn1_part,
+                             int32_t part, int32_t lg, int32_t V, int32_t dim, const uint32_t *cum_table,
+                             float alpha0, float min_alpha, int64_t total_examples, int64_t example_base,
+                             int64_t sent_per_job, int64_t sent_id_base, int32_t neg_group, uint64_t seed,
+                             uint32_t epoch, int64_t *pairs_out)
 {
     pthread_once(&exp_once, build_exp_table);
     enum { FN = 5 };
-    float *out = (float *)malloc(sizeof(float) * (size_t)dim * (FN + 1) * 2 + sizeof(float) * (size_t)dim);
-    if (!out) return -1;
-    float *orig = out + (size_t)dim * (FN + 1), *work = orig + (size_t)dim * (FN + 1);
+    float *work = (float *)malloc(sizeof(float) * (size_t)dim);
+    if (!work) return -1;
     const uint32_t cum_last = cum_table[V - 1];
-    const int64_t n_runs = (n_pairs + K - 1) / K;
-    for (int64_t run = 0; run < n_runs; ++run) {
-        int32_t tg[FN]; int skip_base[FN + 1] = {0};
+    int64_t pairs = 0, p = 0;
+    while (p < n_words) {
+        if (!(words[p] & 0x80000000u)) { free(work); return -2; }
+        const int32_t centre = (int32_t)(words[p] & 0x7FFFFFFFu);
+        const uint32_t s = words[p + 1], pos = words[p + 2] & 0xFFFFu;
+        const int32_t cnt = (int32_t)(words[p + 2] >> 16);
+        const uint64_t gs = (uint64_t)(sent_id_base + (int64_t)s);
+        const uint32_t poskey = neg_group > 1 ? pos / (uint32_t)neg_group : pos;
+        int32_t tg[FN];
         uint32_t rr[4] = {0, 0, 0, 0};
         for (int32_t n = 0; n < FN; ++n) {
-            if ((n & 3) == 0) {
-                uint32_t ctr[4] = { (uint32_t)run, (uint32_t)((uint64_t)run >> 32), tag, (epoch << 8) | (uint32_t)(1 + (n >> 2)) };
-                uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
-                n2v_oracle_philox4x32_10(ctr, key, rr);
-            }
+            if ((n & 3) == 0) philox_words(seed, gs, (poskey << 16) | 0xFFFFu, (epoch << 8) | (uint32_t)(1 + (n >> 2)), rr);
             int32_t t = bisect_left_u32(cum_table, V, rr[n & 3] % cum_last) >> lg;
             if ((((int64_t)t << lg) | part) >= V) --t;
             tg[n] = t;
         }
-        for (int32_t d1 = 0; d1 < FN; ++d1)
-            for (int32_t d2 = d1 + 1; d2 < FN; ++d2) if (tg[d1] == tg[d2]) skip_base[d2 + 1] = 1;
-        for (int32_t d = 1; d <= FN; ++d) {
-            if (skip_base[d]) continue;
-            memcpy(out + (size_t)d * dim, syn1_part + (int64_t)tg[d - 1] * dim, sizeof(float) * (size_t)dim);
-            memcpy(orig + (size_t)d * dim, out + (size_t)d * dim, sizeof(float) * (size_t)dim);
-        }
-        int32_t cur_c = -1;
-        const int64_t p0 = run * K, p1 = p0 + K < n_pairs ? p0 + K : n_pairs;
-        for (int64_t q = p0; q <= p1; ++q) {
-            const int32_t c = q < p1 ? pairs[2 * q] : -2;
-            if (c != cur_c) {
-                if (cur_c >= 0) {
-                    float *row = syn1_part + (int64_t)cur_c * dim;
-                    for (int32_t i = 0; i < dim; ++i) row[i] += out[i] - orig[i];
-                }
-                if (q == p1) break;
-                memcpy(out, syn1_part + (int64_t)c * dim, sizeof(float) * (size_t)dim);
-                memcpy(orig, out, sizeof(float) * (size_t)dim);
-                cur_c = c;
-            }
-            float *row1 = syn0_part + (int64_t)pairs[2 * q + 1] * dim;
-            float g[FN + 1];
-            for (int32_t d = 0; d <= FN; ++d) {
-                g[d] = 0.0f;
-                if (d > 0 && (skip_base[d] || tg[d - 1] == c)) continue;
-                const float *row2 = out + (size_t)d * dim;
+        const int64_t ex = example_base + (int64_t)s;
+        const int64_t job_first = ex - ex % sent_per_job;
+        const double prog = (double)job_first / (double)total_examples;
+        const double al = (double)alpha0 - ((double)alpha0 - (double)min_alpha) * prog;
+        const float alpha = (float)(al > (double)min_alpha ? al : (double)min_alpha);
+        for (int32_t j = 0; j < cnt; ++j) {
+            float *row1 = syn0_part + (int64_t)words[p + 3 + j] * dim;
+            memset(work, 0, sizeof(float) * (size_t)dim);
+            for (int32_t k = 0; k <= FN; ++k) {
+                int32_t target; float label;
+                if (k == 0) { target = centre; label = 1.0f; }
+                else { target = tg[k - 1]; if (target == centre) continue; label = 0.0f; }
+                float *row2 = syn1_part + (int64_t)target * dim;
                 float f = 0.0f;
                 for (int32_t i = 0; i < dim; ++i) f += row1[i] * row2[i];
                 if (f <= -MAX_EXP || f >= MAX_EXP) continue;
                 f = EXP_TABLE[(int)((f + MAX_EXP) * (EXP_TABLE_SIZE / MAX_EXP / 2))];
-                g[d] = ((d == 0 ? 1.0f : 0.0f) - f) * alpha;
-            }
-            memset(work, 0, sizeof(float) * (size_t)dim);
-            for (int32_t d = 0; d <= FN; ++d) {
-                float *row2 = out + (size_t)d * dim;
-                if (d > 0 && skip_base[d]) continue;
-                for (int32_t i = 0; i < dim; ++i) work[i] += g[d] * row2[i];
-                for (int32_t i = 0; i < dim; ++i) row2[i] += g[d] * row1[i];
+                const float g = (label - f) * alpha;
+                for (int32_t i = 0; i < dim; ++i) work[i] += g * row2[i];
+                for (int32_t i = 0; i < dim; ++i) row2[i] += g * row1[i];
             }
             for (int32_t i = 0; i < dim; ++i) row1[i] += work[i];
+            ++pairs;
         }
-        for (int32_t d = 1; d <= FN; ++d) {
-            if (skip_base[d]) continue;
-            float *row = syn1_part + (int64_t)tg[d - 1] * dim;
-            for (int32_t i = 0; i < dim; ++i) row[i] += out[(size_t)d * dim + i] - orig[(size_t)d * dim + i];
-        }
+        p += 3 + cnt;
     }
-    free(out);
+    if (pairs_out) *pairs_out = pairs;
+    free(work);
     return 0;
 }

@@ -1,7 +1,7 @@
 """Link-prediction AUC of the block-partitioned SGNS (BlockSgnsTrainer, all parts on one device =
 exactly what n GPUs compute) on C2, main_link.main protocol (main_link.py:519-565), same graph /
-split / walks as scripts/auc_c2.py. Sweeps parts x run_pairs x pool size.
-   GRID="parts,run,pool;..." SEEDS=3 python scripts/auc_block.py"""
+split / walks as scripts/auc_c2.py. Sweeps parts x neg_group x pool size.
+   GRID="parts,neg_group,pool[,warps];..." SEEDS=3 python scripts/auc_block.py"""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -18,7 +18,7 @@ t = dg.build_alias_tables(0.25, 4.0)
 starts = torch.arange(n, dtype=torch.int32, device="cuda").repeat(R)
 neg = build_neg_samples(n, edges, len(te), seed=1)
 seeds = list(range(1, 1 + int(os.environ.get("SEEDS", "3"))))
-grid = os.environ.get("GRID", "1,16,2048;2,16,4096;4,16,8192;8,16,16384;8,8,16384;8,32,16384;8,16,50000;1,16,50000;8,16,2048")
+grid = os.environ.get("GRID", "1,1,4096;2,1,4096;4,1,4096;8,1,4096;8,1,16384;8,1,1024;2,2,4096;4,4,4096;8,8,4096;8,4,4096;8,2,4096")
 grid = [tuple(int(x) for x in g.split(",")) for g in grid.split(";")]      # optional 4th field: Hogwild width (warps)
 
 
@@ -40,15 +40,15 @@ print("sentence_major_shared", np.mean(out["sentence_major_shared"]), flush=True
 for cfg in grid:
     parts, run, pool = cfg[:3]
     gw = cfg[3] if len(cfg) > 3 else None
-    key = "parts=%d run=%d pool=%d" % (parts, run, pool) + (" warps=%d" % gw if gw else "")
+    key = "parts=%d neg_group=%d pool=%d" % (parts, run, pool) + (" warps=%d" % gw if gw else "")
     for seed in seeds:
         walks = corpora[seed]
         counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=n)
-        trn = BlockSgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=seed, local_parts=parts, run_pairs=run)
+        trn = BlockSgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=seed, local_parts=parts, neg_group=run)
         total = walks.shape[0]
         for a in range(0, total, pool):
             b = min(total, a + pool)
-            trn.train(walks[a:b], None, b - a, L, total_examples=total, example_base=a, sent_id_base=a, grid_warps=gw)
+            trn.train(walks[a:b], None, b - a, L, total_examples=total, example_base=a, sent_id_base=a, sent_per_job=10000 // L, grid_warps=gw)
         trn.check_overflow()
         s0, _ = trn.gather()
         out.setdefault(key, []).append(auc_of(s0, trn.order))

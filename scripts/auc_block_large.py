@@ -1,5 +1,5 @@
 """Block-partitioned SGNS quality at scale, all parts on one GPU (= what n GPUs compute): planted-partition graph with 1 M nodes / 20 M edges, main_link protocol (50 % of the edges
-held out, walks R=5 L=40 p=0.25 q=4 on the rest, d=128, window 10), parts x run_pairs x pool size (walks per pool).
+held out, walks R=5 L=40 p=0.25 q=4 on the rest, d=128, window 10), parts x neg_group x pool size (walks per pool).
    GRID="parts,run,pool;..." python scripts/auc_block_large.py AUC on 1 M held-out edges vs 1 M non-edges."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -54,21 +54,20 @@ def auc_of(tr):
 class _View:
     pass
 
-def run(parts, run_pairs, pool):
-    tr = BlockSgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=1, local_parts=parts, run_pairs=run_pairs)
+def run(parts, neg_group, pool):
+    tr = BlockSgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=1, local_parts=parts, neg_group=neg_group)
     for p0 in range(0, total, pool):
         p1 = min(total, p0 + pool)
         for g0 in range(p0, p1, B):                 # the pool is trained in walk batches of B (pair buffers stay small)
             nb = min(B, p1 - g0); walk(g0, nb)
-            # alpha fixed over the pool, pair streams per batch: same pairs, same schedule per batch
-            tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=p0, sent_id_base=g0)
+            tr.train(walks[:nb], None, nb, L, total_examples=total, example_base=g0, sent_id_base=g0, sent_per_job=10000 // L)
     tr.check_overflow()
     v = _View(); v.vocab_of_id = tr.vocab_of_id; v.syn0, _ = tr.gather()
     return auc_of(v)
 
-grid = os.environ.get("GRID", "1,16,524288;8,16,524288;8,32,524288;2,16,524288;4,16,524288")
+grid = os.environ.get("GRID", "1,1,524288;2,1,524288;4,1,524288;8,1,524288;8,8,524288")
 for cfg in grid.split(";"):
     parts, rp, pool = (int(x) for x in cfg.split(","))
     t0 = time.time()
     a = run(parts, rp, pool)
-    print(json.dumps({"parts": parts, "run_pairs": rp, "pool_walks": pool, "auc": a, "seconds": round(time.time() - t0, 1)}), flush=True)
+    print(json.dumps({"parts": parts, "neg_group": rp, "pool_walks": pool, "auc": a, "seconds": round(time.time() - t0, 1)}), flush=True)

@@ -31,7 +31,7 @@ def train(trainer, walks, per_rank, gw, local_run):
     pool = per_rank * world
     for p0 in range(0, total - pool + 1, pool):
         mine = walks[p0: p0 + pool] if local_run else walks[p0 + rank * per_rank: p0 + (rank + 1) * per_rank]
-        trainer.train(mine.contiguous(), None, mine.shape[0], L, total_examples=total, example_base=p0, sent_id_base=p0, grid_warps=gw)
+        trainer.train(mine.contiguous(), None, mine.shape[0], L, total_examples=total, example_base=p0, sent_id_base=p0, sent_per_job=10000 // L, grid_warps=gw)
     trainer.check_overflow()
     return trainer.gather()
 

@@ -223,29 +223,87 @@ def test_gloo_block_schedule_ring(world):
         assert sorted(r[2][e] for r in res) == list(range(world))
 
 
+def parse_groups(words):
+    """group stream -> int64[n_pairs, 4] rows {centre local row, context local row, sentence, position}"""
+    out, p = [], 0
+    while p < len(words):
+        assert words[p] & 0x80000000
+        c, s, pos, cnt = int(words[p] & 0x7FFFFFFF), int(words[p + 1]), int(words[p + 2] & 0xFFFF), int(words[p + 2] >> 16)
+        assert cnt >= 1 and not (words[p + 3: p + 3 + cnt] & 0x80000000).any()
+        out += [(c, int(x), s, pos) for x in words[p + 3: p + 3 + cnt]]
+        p += 3 + cnt
+    return np.asarray(out, dtype=np.int64).reshape(-1, 4)
+
+
 def test_oracle_block_streams_cover_sentence_major_pairs():
-    """oracle self-consistency: the pair streams of all (centre part, context part) buckets together
-    are exactly the pairs of the sentence-major law under the same Philox addressing."""
+    """oracle self-consistency: the group streams of all (centre part, context part) buckets together
+    are exactly the pairs of the sentence-major law under the same Philox addressing, and with ONE
+    part the block law IS the sentence-major shared-negative law (same draws, same order, same alpha)."""
     import oracle
     z = np.load(os.path.join(ROOT, "tests", "golden", "karate_p025_q4.npz"))
     w = z["walks"]
     voc = oracle.sgns_vocab(w, 34)
     tok = np.where(w >= 0, voc.id2index[np.maximum(w, 0)], -1).astype(np.int32).ravel()
     off = np.arange(w.shape[0] + 1, dtype=np.int64) * w.shape[1]
-    _, _, pairs = oracle.sgns_train(tok, off, voc, dim=8, window=10, negative=5, iters=1, workers=1, rng_mode=3, seed=4)
-    whole = oracle.sgns_make_pairs(tok, off, voc, 0, 1, window=10, seed=4)[0]
+    V, dim = voc.V, 16
+    s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=dim, window=10, negative=5, iters=1, workers=1, rng_mode=3, seed=4)
+    whole = parse_groups(oracle.sgns_make_groups(tok, off, voc, 0, 1, window=10, seed=4)[0])
     assert len(whole) == pairs
     for n_parts in (2, 4, 8):
         got = []
         for k in range(n_parts):
-            for b, st in enumerate(oracle.sgns_make_pairs(tok, off, voc, k, n_parts, window=10, seed=4)):
-                got.append(np.stack([st[:, 0] * n_parts + k, st[:, 1] * n_parts + b], 1))
+            for b, st in enumerate(oracle.sgns_make_groups(tok, off, voc, k, n_parts, window=10, seed=4)):
+                g = parse_groups(st)
+                got.append(np.stack([g[:, 0] * n_parts + k, g[:, 1] * n_parts + b, g[:, 2], g[:, 3]], 1))
         got = np.concatenate(got)
         assert len(got) == pairs
-        key = lambda a: np.sort(a[:, 0].astype(np.int64) * 100000 + a[:, 1])
+        key = lambda a: np.sort(((a[:, 2] * 100 + a[:, 3]) * 64 + a[:, 0]) * 64 + a[:, 1])
         assert np.array_equal(key(got), key(whole))
-    # one part: the block law trains every pair once; tables move and stay finite
-    V, dim = voc.V, 16
     p0 = [oracle.sgns_init_syn0(V, dim, 4)]; p1 = [np.zeros((V, dim), np.float32)]
-    n = oracle.sgns_block_pool(tok, off, voc, p0, p1, window=10, alpha=0.025, run_pairs=16, seed=4)
-    assert n == pairs and np.isfinite(p0[0]).all() and np.abs(p1[0]).max() > 1e-3
+    n = oracle.sgns_block_pool(tok, off, voc, p0, p1, window=10, alpha=0.025, total_examples=w.shape[0],
+                               sent_per_job=10000 // w.shape[1], seed=4)
+    assert n == pairs
+    assert np.array_equal(p0[0], s0) and np.array_equal(p1[0], s1)
+    # several parts: every pair trained once; tables move and stay finite
+    for n_parts in (2, 8):
+        rows = (V + n_parts - 1) // n_parts
+        full0 = oracle.sgns_init_syn0(V, dim, 4)
+        q0 = [np.zeros((rows, dim), np.float32) for _ in range(n_parts)]
+        q1 = [np.zeros((rows, dim), np.float32) for _ in range(n_parts)]
+        for k in range(n_parts):
+            q0[k][: len(full0[k::n_parts])] = full0[k::n_parts]
+        n = oracle.sgns_block_pool(tok, off, voc, q0, q1, window=10, alpha=0.025, total_examples=w.shape[0],
+                                   sent_per_job=10000 // w.shape[1], seed=4)
+        assert n == pairs and all(np.isfinite(x).all() for x in q0) and max(np.abs(x).max() for x in q1) > 1e-3
+
+
+def test_reference_main_py_binds_to_the_dropins_without_a_gpu():
+    """src/main.py executed unmodified (runpy) with the drop-ins first on sys.path: argparse, read_graph and
+    `import node2vec` / `from gensim.models import Word2Vec` resolve to this package, and without a CUDA
+    device the first compute call fails loudly (no CPU fallback) -- the GPU flavour of this test is
+    tests/test_gpu_api.py::test_reference_main_py_runs_unmodified_with_the_dropins."""
+    import runpy
+    import torch
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "src", "main.py")):
+        pytest.skip("reference tree not mounted here")
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU flavour")
+    from node2vec_by_ecc_b200._lib import N2VError
+    argv, cwd = sys.argv, os.getcwd()
+    sys.path.insert(0, os.path.join(ROOT, "node2vec_by_ecc_b200", "dropin"))
+    for m in ("node2vec", "gensim", "gensim.models", "gensim.models.word2vec"):
+        sys.modules.pop(m, None)
+    try:
+        os.chdir(ref)
+        sys.argv = ["main.py", "--input", "graph/karate.edgelist"]
+        with pytest.raises(N2VError, match="no CUDA device"):
+            runpy.run_path(os.path.join(ref, "src", "main.py"), run_name="__main__")
+        import node2vec
+        assert node2vec.Graph.__module__ == "node2vec_by_ecc_b200.walker"
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        sys.path.pop(0)
+        for m in ("node2vec", "gensim", "gensim.models", "gensim.models.word2vec"):
+            sys.modules.pop(m, None)

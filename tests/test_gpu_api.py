@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import torch
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -39,6 +40,28 @@ def test_main_py_pipeline_with_dropins():
         model = Word2Vec(sents, size=128, window=10, min_count=0, sg=1, workers=8, iter=1)
         assert model.wv.syn0.shape == (34, 128)
         assert set(model.wv.vocab.keys()) == {str(v) for v in nx_G.nodes()}
+        # the one-shot map objects were recognised as rows of the device corpus (nothing was stringified):
+        # same tables as training on the corpus object, and as the generic string path
+        assert model._corpus[0] is walks.walks
+        direct = Word2Vec(walks, size=128, window=10, min_count=0, sg=1, workers=8, iter=1, hogwild_warps=1)
+        seq = Word2Vec([map(str, walk) for walk in walks], size=128, window=10, min_count=0, sg=1, workers=8, iter=1,
+                       hogwild_warps=1)
+        generic = Word2Vec([[str(t) for t in walk] for walk in walks], size=128, window=10, min_count=0, sg=1, workers=8,
+                           iter=1, hogwild_warps=1)
+        assert np.array_equal(seq.wv.syn0, direct.wv.syn0) and seq.wv.index2word == direct.wv.index2word
+        assert seq.pairs_trained == generic.pairs_trained
+        for w in ("1", "34", "17"):
+            assert np.allclose(seq.wv[w], generic.wv[w], atol=1e-6)
+        # a shuffled / partial list of rows still trains on the device (row gather), a consumed row does not
+        import random
+        part = [map(str, walk) for walk in walks][::2]
+        random.Random(3).shuffle(part)
+        m2 = Word2Vec(part, size=64, window=5, min_count=0, sg=1, iter=1)
+        assert m2.corpus_count == 170 and m2._corpus[0].shape == (170, 80)
+        used = [map(str, walk) for walk in walks]
+        next(used[5])
+        m3 = Word2Vec(used, size=64, window=5, min_count=0, sg=1, iter=1)
+        assert m3.corpus_count == 340 and m3._corpus[2] == 0          # generic path (ragged token stream)
         # reference dict views of the tables
         J, q = G.alias_nodes[1]
         assert len(J) == nx_G.degree(1) and np.allclose(q, 1.0)
@@ -48,6 +71,34 @@ def test_main_py_pipeline_with_dropins():
         assert (J == J2).all() and (q == q2).all()
     finally:
         sys.path.pop(0)
+
+
+def test_incremental_training_and_device_graph_constructor():
+    """gensim's build_vocab + train(new_sentences) on the existing vocabulary, and node2vec.Graph over a
+    DeviceGraph (graphs that never exist as networkx objects) with bulk start nodes: the calls bench.py's
+    e2e leg makes"""
+    from node2vec_by_ecc_b200 import DeviceGraph, Graph, Word2Vec
+    e = np.asarray(list(karate_nx().edges()), dtype=np.int64) - 1
+    dg = DeviceGraph.from_coo(e[:, 0], e[:, 1], None, 34, undirected=True)
+    G = Graph(dg, False, 0.5, 2.0, seed=3, mode="reject")
+    G.preprocess_transition_probs()
+    every = G.simulate_walks(1, 20)
+    assert len(every) == 34 and [w[0] for w in every] == list(range(34))
+    model = Word2Vec(size=64, window=5, min_count=0, sg=1, workers=4, iter=1)
+    model.build_vocab(every)
+    first = model.wv.syn0.copy()
+    for step in range(3):
+        nodes = np.arange(34, dtype=np.int32)[::-1].copy()
+        walks = G.simulate_walks(4, 20, nodes=torch.as_tensor(nodes))
+        assert len(walks) == 136 and walks[0][0] == 33
+        model.train([map(str, w) for w in walks], total_examples=len(walks), epochs=1, start_alpha=0.025 - 0.005 * step,
+                    end_alpha=0.02 - 0.005 * step)
+    assert model.pairs_trained > 3 * 136 * 50 and model.train_count == 3
+    assert np.abs(model.wv.syn0 - first).max() > 1e-3 and np.isfinite(model.wv.syn0).all()
+    # sentences in another id space (strings): mapped through the vocabulary, unknown words ignored
+    before = model.pairs_trained
+    model.train([["1", "2", "zzz", "3", "2", "1"]] * 10, total_examples=10, epochs=1)
+    assert 0 < model.pairs_trained - before <= 10 * 20
 
 
 def test_graph_matches_golden_through_public_api():
@@ -70,6 +121,31 @@ def test_graph_matches_golden_through_public_api():
     G3.preprocess_transition_probs()
     w3 = G3.simulate_walks(2, 30)
     assert len(w3) == 68 and all(len(w) == 30 for w in w3)
+
+
+def test_reference_main_py_runs_unmodified_with_the_dropins():
+    """src/main.py:92-103 executed as a script (runpy), byte for byte, with node2vec_by_ecc_b200/dropin
+    first on sys.path -- where the reference tree is mounted (the build container; not the GPU box)"""
+    import runpy
+    import pytest
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "src", "main.py")):
+        pytest.skip("reference tree not mounted here")
+    argv, cwd = sys.argv, os.getcwd()
+    sys.path.insert(0, os.path.join(ROOT, "node2vec_by_ecc_b200", "dropin"))
+    for m in ("node2vec", "gensim", "gensim.models", "gensim.models.word2vec"):
+        sys.modules.pop(m, None)
+    try:
+        os.chdir(ref)
+        sys.argv = ["main.py", "--input", "graph/karate.edgelist", "--num-walks", "4", "--walk-length", "30"]
+        ns = runpy.run_path(os.path.join(ref, "src", "main.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        sys.argv = argv
+        sys.path.pop(0)
+    emb = ns["emb"]
+    assert emb.wv.syn0.shape == (34, 128) and np.isfinite(emb.wv.syn0).all()
+    assert set(emb.wv.vocab.keys()) == {str(v) for v in range(1, 35)}
 
 
 def test_graph_survives_pickle():
@@ -281,6 +357,39 @@ def test_walk_file_device_parser_equals_generic_path(tmp_path):
     p2.write_text("a b c\nb c d\n")
     m2 = Word2Vec(LineSentence(str(p2)), size=8, window=2, min_count=0, sg=1, iter=1, hogwild_warps=1)
     assert sorted(m2.wv.index2word) == ["a", "b", "c", "d"]
+
+
+def test_fused_similarity_selections_at_sampled_threshold_sizes():
+    """sizes at which the thresholds come from a sample (scoring.py): global top-k over 4 M candidate
+    pairs and per-user top share over 6,000 users, both exact against numpy"""
+    from node2vec_by_ecc_b200 import KeyedVectors, Vocab
+    from node2vec_by_ecc_b200.augment import user_edges
+    rng = np.random.RandomState(7)
+    V, d = 6000, 64
+    kv = KeyedVectors(d)
+    kv.index2word = [str(i) for i in range(V)]
+    kv.vocab = {w: Vocab(i, 1) for i, w in enumerate(kv.index2word)}
+    base = rng.randn(40, d).astype(np.float32)                 # clustered rows: a heavy upper tail of scores
+    kv.syn0 = (base[rng.randint(0, 40, V)] + 0.7 * rng.randn(V, d)).astype(np.float32)
+    e = kv.syn0 / np.linalg.norm(kv.syn0, axis=1, keepdims=True)
+    users, items = [str(i) for i in range(2000)], [str(i) for i in range(2000, 4100)]
+    train = [(str(rng.randint(0, 2000)), str(rng.randint(2000, 4100))) for _ in range(3000)]
+    got = kv.top_k_links(users, items, k=1000, exclude=train)
+    S = e[:2000] @ e[2000:4100].T
+    for a, b in train:
+        S[int(a), int(b) - 2000] = -np.inf
+    flat = np.argsort(-S.ravel(), kind="stable")[:1000]
+    gs = np.asarray([s for _, s in got])
+    assert np.allclose(gs, S.ravel()[flat], atol=2e-6)
+    want = {(str(i // 2100), str(2000 + i % 2100)) for i in flat[:990]}     # the last few may tie within float32 round-off
+    assert len(want - {p for p, _ in got}) <= 2
+    k = int(V * 0.01)
+    src, dst, w = user_edges(kv, list(range(V)), "relu-ratio", 0.01, "cos")
+    assert src.numel() == V * k and bool((src.view(V, k) == torch.arange(V, device=src.device)[:, None]).all())
+    M = e @ e.T
+    np.fill_diagonal(M, 0.0)
+    kth = -np.sort(-M, axis=1)[:, :k]
+    assert np.allclose(w.view(V, k).cpu().numpy(), kth, atol=2e-6)
 
 
 def test_user_edge_augmentation_matches_brute_force():

@@ -1,6 +1,6 @@
 """Block-partitioned SGNS (csrc/n2v_sgns_block.cu, word2vec.BlockSgnsTrainer) against the oracle's
-restatement of the same schedule (oracle/sgns_oracle.c: sgns_oracle_make_pairs /
-sgns_oracle_block_train): pair streams bit-exact, tables within float tolerance when the device runs
+restatement of the same schedule (oracle/sgns_oracle.c: sgns_oracle_make_groups /
+sgns_oracle_train_groups): group streams bit-exact, tables within float tolerance when the device runs
 one warp (sequential order); all parts on one device == what n GPUs would compute."""
 import numpy as np
 import pytest
@@ -28,30 +28,46 @@ def oracle_tokens(walks_np, id2index):
     return tok, off
 
 
-def make_trainer(walks, n_ids, n_parts, dim=128, seed=4, run_pairs=16):
+def make_trainer(walks, n_ids, n_parts, dim=128, seed=4, neg_group=1):
     from node2vec_by_ecc_b200 import BlockSgnsTrainer
     counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=n_ids)
     return BlockSgnsTrainer(counts, dim=dim, window=10, negative=5, sample=1e-3, seed=seed, local_parts=n_parts,
-                            run_pairs=run_pairs)
+                            neg_group=neg_group)
+
+
+def split_parts(full, W, rows):
+    parts = [np.zeros((rows, full.shape[1]), np.float32) for _ in range(W)]
+    for k in range(W):
+        parts[k][: len(full[k::W])] = full[k::W]
+    return parts
+
+
+def join_parts(parts, V):
+    W = len(parts)
+    full = np.zeros((V, parts[0].shape[1]), np.float32)
+    for k in range(W):
+        full[k::W] = parts[k][: (V - k + W - 1) // W]
+    return full
 
 
 @pytest.mark.parametrize("n_parts", [1, 2, 4, 8])
-def test_pair_streams_equal_oracle(n_parts):
+def test_group_streams_equal_oracle(n_parts):
     z, g, corpus = corpus_from_golden("karate_p025_q4")
     walks = corpus.walks
     tr = make_trainer(walks, g.n, n_parts)
     voc, id2index = oracle_vocab(tr, g.n)
     tok, off = oracle_tokens(z["walks"], id2index)
     P = tr._params(0, 1)
-    total = 0
+    pairs = 0
     for k in range(n_parts):
-        pairs, bounds = tr.make_pairs(walks, None, walks.shape[0], walks.shape[1], 1000, P, k)
-        want = oracle.sgns_make_pairs(tok, off, voc, k, n_parts, window=10, seed=4, epoch=0, sent_id_base=1000)
-        got = pairs.cpu().numpy()
+        words, bounds = tr.make_groups(walks, None, walks.shape[0], walks.shape[1], 1000, P, k)
+        want = oracle.sgns_make_groups(tok, off, voc, k, n_parts, window=10, seed=4, epoch=0, sent_id_base=1000)
+        got = words.cpu().numpy().view(np.uint32)
         for b in range(n_parts):
             assert bounds[b + 1] - bounds[b] == len(want[b])
             assert np.array_equal(got[bounds[b]:bounds[b + 1]], want[b])
-        total += bounds[-1]
+            st = want[b]
+            pairs += int((st[np.nonzero(st & 0x80000000)[0] + 2] >> 16).sum()) if len(st) else 0
     tr.check_overflow()
     # the streams of all parts together are the pairs of the sentence-major trainer (same Philox law)
     from node2vec_by_ecc_b200 import SgnsTrainer
@@ -59,10 +75,10 @@ def test_pair_streams_equal_oracle(n_parts):
                       sample=1e-3, seed=4)
     ref.train(walks, None, walks.shape[0], walks.shape[1], total_examples=walks.shape[0], sent_id_base=1000,
               negative_sharing=1)
-    assert int(ref.pairs[0]) == total
+    assert int(ref.pairs[0]) == pairs
 
 
-def test_pair_streams_ragged_long_sentences():
+def test_group_streams_ragged_long_sentences():
     """sent_off corpus with sentences longer than the staging buffer (streamed in chunks)"""
     rng = np.random.default_rng(5)
     n_ids, lens = 300, rng.integers(0, 900, size=40)
@@ -77,45 +93,81 @@ def test_pair_streams_ragged_long_sentences():
     P = tr._params(2, 1)
     off_d = torch.as_tensor(off).cuda()
     for k in range(4):
-        pairs, bounds = tr.make_pairs(walks, off_d, len(lens), 0, 7, P, k)
-        want = oracle.sgns_make_pairs(tok, off, voc, k, 4, window=10, seed=4, epoch=2, sent_id_base=7)
-        got = pairs.cpu().numpy()
+        words, bounds = tr.make_groups(walks, off_d, len(lens), 0, 7, P, k)
+        want = oracle.sgns_make_groups(tok, off, voc, k, 4, window=10, seed=4, epoch=2, sent_id_base=7)
+        got = words.cpu().numpy().view(np.uint32)
         for b in range(4):
             assert np.array_equal(got[bounds[b]:bounds[b + 1]], want[b])
 
 
-@pytest.mark.parametrize("n_parts,dim,run_pairs", [(1, 128, 16), (2, 128, 16), (4, 64, 7), (8, 128, 32)])
-def test_block_schedule_sequential_equals_oracle(n_parts, dim, run_pairs):
+@pytest.mark.parametrize("n_parts,dim,neg_group,warps", [(1, 128, 1, 1), (2, 128, 1, 1), (4, 64, 1, 1), (8, 128, 1, 1),
+                                                        (4, 128, 3, 1), (2, 128, 1, 3)])
+def test_block_schedule_sequential_equals_oracle(n_parts, dim, neg_group, warps):
+    """one warp per launch == the oracle's restatement of the schedule, two pools (alpha moves on);
+    with 3 warps the order differs only by which contiguous third of a stream goes first -- on karate
+    the thirds share rows, so that case only checks pair counts and closeness"""
     z, g, corpus = corpus_from_golden("karate_p025_q4")
     walks = corpus.walks
-    tr = make_trainer(walks, g.n, n_parts, dim=dim, run_pairs=run_pairs)
+    tr = make_trainer(walks, g.n, n_parts, dim=dim, neg_group=neg_group)
     voc, id2index = oracle_vocab(tr, g.n)
     tok, off = oracle_tokens(z["walks"], id2index)
     W, V = n_parts, tr.V
     rows = (V + W - 1) // W
-    full0 = oracle.sgns_init_syn0(V, dim, 4)
-    parts0 = [np.zeros((rows, dim), np.float32) for _ in range(W)]
+    parts0 = split_parts(oracle.sgns_init_syn0(V, dim, 4), W, rows)
     parts1 = [np.zeros((rows, dim), np.float32) for _ in range(W)]
-    for k in range(W):
-        parts0[k][: len(full0[k::W])] = full0[k::W]
     half = walks.shape[0] // 2
     n_tot = walks.shape[0]
+    L = walks.shape[1]
     pairs = 0
-    for pool, (a, b) in enumerate([(0, half), (half, n_tot)]):        # two pools: alpha and the tag move on
-        tr.train(walks[a:b], None, b - a, walks.shape[1], total_examples=n_tot, example_base=a, sent_id_base=a, grid_warps=1)
-        alpha = tr.pool_alpha(a, n_tot)
-        pairs += oracle.sgns_block_pool(tok[a * walks.shape[1]: b * walks.shape[1]], off[: b - a + 1], voc, parts0, parts1,
-                                        window=10, alpha=alpha, run_pairs=run_pairs, seed=4, epoch=0, sent_id_base=a, pool=pool)
+    for a, b in [(0, half), (half, n_tot)]:
+        tr.train(walks[a:b], None, b - a, L, total_examples=n_tot, example_base=a, sent_id_base=a, sent_per_job=25,
+                 grid_warps=warps)
+        pairs += oracle.sgns_block_pool(tok[a * L: b * L], off[: b - a + 1], voc, parts0, parts1, window=10,
+                                        alpha=0.025, total_examples=n_tot, example_base=a, sent_per_job=25,
+                                        neg_group=neg_group, seed=4, epoch=0, sent_id_base=a)
     tr.check_overflow()
     assert int(tr.pairs[0]) == pairs
     s0, s1 = tr.gather()
-    want0 = np.zeros((V, dim), np.float32); want1 = np.zeros((V, dim), np.float32)
-    for k in range(W):
-        n_k = (V - k + W - 1) // W
-        want0[k::W] = parts0[k][:n_k]; want1[k::W] = parts1[k][:n_k]
-    assert np.abs(s0.cpu().numpy() - want0).max() < 2e-4
-    assert np.abs(s1.cpu().numpy() - want1).max() < 2e-4
+    want0, want1 = join_parts(parts0, V), join_parts(parts1, V)
+    tol = 2e-4 if warps == 1 else 0.05
+    assert np.abs(s0.cpu().numpy() - want0).max() < tol
+    assert np.abs(s1.cpu().numpy() - want1).max() < tol
     assert np.abs(want1).max() > 1e-3
+
+
+def test_one_part_equals_the_sentence_major_kernel():
+    """the block law does not depend on the partition: with one part (and one warp) the group kernel
+    reproduces n2v_sgns_train's shared-negative run -- same draws, same order, same job alpha"""
+    from node2vec_by_ecc_b200 import SgnsTrainer
+    z, g, corpus = corpus_from_golden("karate_p025_q4")
+    walks = corpus.walks
+    counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=g.n)
+    ref = SgnsTrainer(counts, dim=128, window=10, negative=5, sample=1e-3, seed=4)
+    ref.train(walks, None, walks.shape[0], walks.shape[1], total_examples=walks.shape[0], sent_per_job=40,
+              grid_warps=1, negative_sharing=1)
+    tr = make_trainer(walks, g.n, 1)
+    tr.train(walks, None, walks.shape[0], walks.shape[1], total_examples=walks.shape[0], sent_per_job=40, grid_warps=1)
+    s0, s1 = tr.gather()
+    assert int(tr.pairs[0]) == int(ref.pairs[0])
+    assert float((s0 - ref.syn0).abs().max()) < 1e-6 and float((s1 - ref.syn1neg).abs().max()) < 1e-6
+
+
+def test_device_side_bounds_equal_host_bounds():
+    """exact_bounds=False: from the second pool of a size on, the stream bounds never leave the device"""
+    z, g, corpus = corpus_from_golden("karate_p025_q4")
+    walks = corpus.walks
+    n, L = walks.shape[0] // 4, walks.shape[1]
+    res = []
+    for exact in (True, False):
+        tr = make_trainer(walks, g.n, 2)
+        for i in range(4):
+            tr.train(walks[i * n:(i + 1) * n], None, n, L, total_examples=4 * n, example_base=i * n, sent_id_base=i * n,
+                     grid_warps=1, exact_bounds=exact)
+        tr.check_overflow()
+        res.append((int(tr.pairs[0]), tr.gather()))
+        assert exact or tr._buf[0]["cap"] >= int(tr._buf[0]["need"] * 1.5)
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1][0], res[1][1][0]) and torch.equal(res[0][1][1], res[1][1][1])
 
 
 def test_block_wide_close_to_sequential():
@@ -147,3 +199,18 @@ def test_two_ranks_equal_one_device():
     d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert d["max_abs_diff_vs_one_device"] == [0.0, 0.0] and d["moved"] > 1e-3
     assert d["auc_mean"] > 0.78
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_reference_facing_calls_on_two_gpus():
+    """Graph(..., distributed=True).simulate_walks + Word2Vec([map(str, walk) ...]) under torchrun x 2: walks
+    sharded by start node, block-partitioned training, AUC on C2 (band checked at 0.01 here: 3 seeds)"""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(root, "scripts", "dist_api_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["world"] == 2 and d["trainer"] == "BlockSgnsTrainer" and d["walks_per_rank"] == [25000] * 3
+    assert d["corpus_count"] == 50000 and d["pairs"] > 1.5e7 and 0.78 < d["auc_mean"] < 0.81

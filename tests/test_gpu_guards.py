@@ -95,18 +95,18 @@ def test_argument_guards_of_the_block_and_packed_entry_points():
     tr = BlockSgnsTrainer(counts, dim=64, local_parts=2)
     P = tr._params(0, 4)
     P.dim = 50
-    pairs = torch.zeros((8, 2), dtype=torch.int32, device="cuda")
+    words = torch.zeros(16, dtype=torch.int32, device="cuda")
     with pytest.raises(N2VError, match="multiple of 4"):
-        check(lib().n2v_sgns_train_block(ptr(pairs), C.c_int64(8), ptr(tr.cum_table), ptr(tr.bucket_lo), C.byref(P),
-                                         C.c_float(0.025), C.c_int32(8), C.c_uint32(0), ptr(tr.parts0[0]), ptr(tr.parts1[0]),
-                                         C.c_int32(0), C.c_int32(2), ptr(tr.pairs), stream()))
+        check(lib().n2v_sgns_train_groups(ptr(words), C.c_int64(0), C.c_int64(16), None, None, C.c_int64(16), C.c_int64(0),
+                                          ptr(tr.cum_table), ptr(tr.bucket_lo), C.byref(P), C.c_int32(1), ptr(tr.parts0[0]),
+                                          ptr(tr.parts1[0]), C.c_int32(0), C.c_int32(2), ptr(tr.pairs), stream()))
     P = tr._params(0, 4)
     P.window = 113                     # used to spin forever on sentences with > 256 kept tokens
     tok = torch.zeros((2, 400), dtype=torch.int32, device="cuda")
     off = torch.zeros(2 * 2 + 1, dtype=torch.int64, device="cuda")
-    ws = torch.empty(int(lib().n2v_sgns_pairs_workspace_bytes(C.c_int64(2), C.c_int32(2))), dtype=torch.uint8, device="cuda")
+    ws = torch.empty(int(lib().n2v_sgns_groups_workspace_bytes(C.c_int64(2), C.c_int32(2))), dtype=torch.uint8, device="cuda")
     with pytest.raises(N2VError, match="window"):
-        check(lib().n2v_sgns_pairs_count(ptr(tok), None, C.c_int64(2), C.c_int32(400), C.c_int64(0), None, None, C.byref(P),
+        check(lib().n2v_sgns_groups_count(ptr(tok), None, C.c_int64(2), C.c_int32(400), C.c_int64(0), None, None, C.byref(P),
                                          C.c_int32(0), C.c_int32(2), ptr(off), ptr(ws), C.c_size_t(ws.numel()), stream()))
     dummy = torch.zeros(64, dtype=torch.int64, device="cuda")
     w = torch.zeros((4, 2), dtype=torch.int32, device="cuda")
