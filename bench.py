@@ -36,14 +36,41 @@ if ROOT not in sys.path:
 
 BYTES_PER_PAIR = 7168        # 2 x 512 B x (1 input + 1 positive + 5 negative rows)
 BYTES_PER_ALIAS_STEP = 40
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the default bench step, from the
-# committed `ncu --set full` captures (profiles/): filled in when a capture exists, else null
-NCU_TRAFFIC = {     # bytes per launch at the default workload (2^19 walks per launch)
-    "sgns_train_kernel_v3": 189.8e9,          # profiles/r01_j_sgns_v3_ncu_full.json (91.6 GB read + 98.2 GB written)
-    "sgns_train_kernel_v2": None,
-    "walk_reject_indexed_kernel": 28.43e9,    # profiles/r01_j_walk_reject_indexed_ncu_full.json
-    "walk_reject_kernel": 41.26e9,            # profiles/r01_a_walk_reject_ncu_full.json
+KERNEL_SOURCES = {     # the files a kernel is compiled from: a capture is valid only for these exact sources
+    "sgns_train_kernel_v3": ["n2v_sgns.cu", "n2v_sgns_stage.cuh", "n2v_common.cuh"],
+    "sgns_train_kernel_v2": ["n2v_sgns.cu", "n2v_sgns_stage.cuh", "n2v_common.cuh"],
+    "sgns_group_kernel": ["n2v_sgns_block.cu", "n2v_sgns_stage.cuh", "n2v_common.cuh"],
+    "walk_reject_indexed_kernel": ["n2v_walk2.cu", "n2v_reject.cuh", "n2v_common.cuh"],
+    "walk_reject_kernel": ["n2v_walk.cu", "n2v_reject.cuh", "n2v_common.cuh"],
+    "walk_alias_kernel": ["n2v_walk.cu", "n2v_common.cuh"],
 }
+
+
+def source_sha16(kernel):
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES.get(kernel, []):
+        with open(os.path.join(ROOT, "node2vec_by_ecc_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, workload_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    of this kernel on this workload (profiles/ncu_traffic.json, written by scripts/capture_traffic.py).
+    A capture taken from other kernel sources than the ones on disk is refused: -> (None, why)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(kernel)
+    except Exception:
+        ent = None
+    if not ent:
+        return None, "no ncu --set full capture of this kernel is committed"
+    if ent.get("source_sha16") != source_sha16(kernel):
+        return None, "stale: %s was captured from other kernel sources (%s)" % (ent.get("profile"), ent.get("source_sha16"))
+    if ent.get("workload") != workload_key:
+        return None, "capture %s is of another workload (%s)" % (ent.get("profile"), ent.get("workload"))
+    return float(ent["dram_bytes_per_launch"]), ent.get("profile")
 
 
 def parse():
@@ -235,20 +262,12 @@ def run_ours(a):
     else:
         sync_walks = min(B, sync_walks_per_rank(trainer.V, world, pairs_per_walk))
 
-    def step(i, host_io=None, record=False):
+    def step(i, record=False):
         g0 = (i * world + rank) * B                         # global id of this rank's first walk
-        if host_io is not None:                              # e2e: inputs from pinned host memory
-            hs, hw, hl, hp, dst = host_io
-            np.copyto(hs.numpy(), ((g0 + np.arange(B, dtype=np.int64)) % n).astype(np.int32))
-            starts = dst.copy_(hs, non_blocking=True)
-        else:
-            starts = ((g0 + ar) % n).to(torch.int32)
+        starts = ((g0 + ar) % n).to(torch.int32)
         e0, e1 = ev(), ev()
         e0.record(); do_walk(starts, g0); e1.record()
-        if host_io is not None:                              # simulate_walks returns to the host,
-            hw.copy_(walks, non_blocking=True); hl.copy_(lens, non_blocking=True)   # learn_embeddings
-            walks.copy_(hw, non_blocking=True)               # takes them back in
-        # SGNS in sub-batches of `sync_walks`, tables combined (delta-sum) after each (N > 1)
+        # SGNS in sub-batches of `sync_walks`, tables combined (delta-sum) after each (N > 1, replica mode)
         for sa in range(0, B, sync_walks):
             sb_ = min(B, sa + sync_walks)
             e2, e3 = ev(), ev()
@@ -267,9 +286,6 @@ def run_ours(a):
                 replica_sync.sync()
             if record:
                 kern["sgns"].append((e2, e3))
-        if host_io is not None:
-            hp.copy_(trainer.pairs[:1], non_blocking=True)
-            torch.cuda.current_stream().synchronize()        # the caller reads the result
         if record:
             kern["walk"].append((e0, e1))
 
@@ -279,14 +295,14 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(first_step, host_io=None, record=False):
+    def timed(first_step, record=False):
         p0 = trainer.pairs.clone()
         c0 = counters.clone()
         barrier()
         s, e = ev(), ev()
         s.record()
         for i in range(first_step, first_step + a.steps):
-            step(i, host_io, record)
+            step(i, record)
         e.record()
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
@@ -324,18 +340,56 @@ def run_ours(a):
 
     e2e = None
     if not a.no_e2e:
-        hs = torch.empty(B, dtype=torch.int32).pin_memory()
+        # the same step through the reference-facing classes (the calls of src/main.py:92-101): start nodes
+        # come from pinned host memory, node2vec.Graph.simulate_walks walks them, the walks go back to the
+        # host (what main_link.py:544-546 writes to the walk file) and gensim-style Word2Vec.train learns
+        # from the corpus object simulate_walks returned; the pair count is read back every step.
+        from node2vec_by_ecc_b200 import Graph, Word2Vec
+        G = Graph(dg, False, a.p, a.q, seed=1, mode=a.walk_mode, distributed=world > 1)
+        G.preprocess_transition_probs()
+        model = Word2Vec(size=a.dim, window=a.window, min_count=0, sg=1, workers=8, iter=1, negative=a.negative,
+                         shared_negatives=a.shared_negatives, atomic_updates=a.atomic)
+        model.build_vocab(G.simulate_walks(1, L))                  # scan_vocab over one walk per node
+        T = model.trainer
+        hs = torch.empty(B * world, dtype=torch.int32).pin_memory()
         hw = torch.empty((B, L), dtype=torch.int32).pin_memory()
         hl = torch.empty(B, dtype=torch.int32).pin_memory()
         hp = torch.empty(1, dtype=torch.int64).pin_memory()
-        dst = torch.empty(B, dtype=torch.int32, device=dev)
-        io = (hs, hw, hl, hp, dst)
-        step(a.warmup + a.steps, io)                                        # warm the pinned path
-        ms_e, pairs_e, _, _ = timed(a.warmup + a.steps + 1, host_io=io)
+        alpha_at = lambda i: max(1e-4, 0.025 - (0.025 - 1e-4) * ((i * world * B) % total_walks) / total_walks)
+
+        def api_step(i):
+            g0 = i * world * B
+            np.copyto(hs.numpy(), ((g0 + np.arange(B * world, dtype=np.int64)) % n).astype(np.int32))
+            corpus = G.simulate_walks(1, L, nodes=hs)              # H2D of the start nodes inside
+            hw.copy_(corpus.walks, non_blocking=True); hl.copy_(corpus.lens, non_blocking=True)
+            model.train(corpus, total_examples=len(corpus), epochs=1, start_alpha=alpha_at(i), end_alpha=alpha_at(i + 1))
+            hp.copy_(T.pairs[:1], non_blocking=True)
+            torch.cuda.current_stream().synchronize()              # the caller reads the result
+
+        first = a.warmup + a.steps
+        for i in range(first, first + 2):                          # warm the pinned path and the allocator
+            api_step(i)
+        p0 = T.pairs.clone()
+        barrier()
+        s_, e_ = ev(), ev()
+        s_.record()
+        for i in range(first + 2, first + 2 + a.steps):
+            api_step(i)
+        e_.record()
+        barrier()
+        ms_e = torch.tensor([s_.elapsed_time(e_)], dtype=torch.float64, device=dev)
+        pr_e = (T.pairs - p0)[:1].clone()
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX); dist.all_reduce(pr_e)
+        ms_e, pairs_e = float(ms_e.item()), int(pr_e.item())
         e2e = {"value": pairs_e / (ms_e / 1e3), "unit": "pairs/s",
-               "h2d_bytes_per_step": (B * 4 + B * L * 4) * world, "d2h_bytes_per_step": (B * L * 4 + B * 4 + 8) * world,
+               "h2d_bytes_per_step": B * world * 4 * world, "d2h_bytes_per_step": (B * L * 4 + B * 4 + 8) * world,
                "ms_per_step": ms_e / a.steps,
-               "api": "DeviceGraph.walk_reject -> host -> %s.train (pinned host buffers)" % type(trainer).__name__}
+               "api": "node2vec.Graph(...).simulate_walks(1, L, nodes=<pinned host array>) -> walks copied to pinned host "
+                      "memory -> Word2Vec.train(corpus, total_examples=, epochs=1, start_alpha=, end_alpha=) -> pair count "
+                      "read back; trainer " + type(T).__name__}
+        del model, G, T
+        torch.cuda.empty_cache()
 
     other = None
     if not a.no_e2e and not peer and not block:      # the other negative-sampling mode, same steps, kernel-timed
@@ -355,30 +409,49 @@ def run_ours(a):
     if rank == 0:
         peak, src = peaks()
         k_ms = sgns_ms
+        wkey = "scale %d edges %d batch %d L %d world %d" % (a.scale, int(a.edges), B, L, world)
         if block:
-            # block kernel: per pair the input row, per carried output row (centre changes + the 5
-            # negatives of a run) one read + one reduction: 1,024 B each; `centres` = carried rows
+            # group kernel: per pair the input row, per carried output row (one centre row per group + 5 per
+            # negative set) one read + one reduction: 1,024 B each; `centres` = carried rows
             alg_bytes = (my_pairs_rank + centres / world) * 1024.0
-            kname = "sgns_group_kernel (block-partitioned tables, neg_group %d)" % a.neg_group
+            kshort = "sgns_group_kernel"
+            kname = "sgns_group_kernel (block-partitioned tables, one negative set per centre occurrence)"
             k_ms = phases["train"]
         elif a.shared_negatives:
             # shared-negative kernel: per pair the input row (read + written, 1,024 B), per centre
             # the 6 carried output rows (read + written once, 6,144 B)
             alg_bytes = (my_pairs_rank * 1024.0 + centres / world * 6144.0)
-            kname = "sgns_train_kernel_v3 (shared negatives)"
+            kshort = "sgns_train_kernel_v3"
+            kname = "sgns_train_kernel_v3 (one negative set per centre occurrence)"
         else:
             alg_bytes = my_pairs_rank * float(BYTES_PER_PAIR)
-            kname = "sgns_train_kernel_v2 (per-pair negatives)"
+            kshort = "sgns_train_kernel_v2"
+            kname = "sgns_train_kernel_v2 (per-pair negatives, gensim's law)"
         n_launch = max(1, len(kern["sgns"])) * (world if block else 1)
         sg_gbs = alg_bytes / (k_ms / 1e3) / 1e9
+        traffic, traffic_src = ncu_traffic(kshort, wkey)
+        gb_8d = my_pairs_rank * BYTES_PER_PAIR / (k_ms / 1e3) / 1e9
+        shared_law = bool(a.shared_negatives)
         roof = {"kernel": kname, "bound": "hbm", "achieved": sg_gbs, "peak": peak, "unit": "GB/s",
-                "frac": sg_gbs / peak, "traffic": NCU_TRAFFIC.get(kname.split()[0]) if (a.scale == 22 and a.batch_walks == 1 << 19 and world == 1) else None,
+                "frac": sg_gbs / peak,
+                # the same kernel time against three byte counts:
+                "frac_model": sg_gbs / peak,          # this kernel's own algorithmic bytes (rows it must move)
+                "frac_8d": None if shared_law else gb_8d / peak,      # 7,168 B/pair, fresh negatives per pair
+                "frac_8d_note": ("n/a: 7,168 B/pair assumes 5 fresh negative rows per pair; this kernel shares one set per "
+                                 "centre occurrence, so it does not move those bytes (it would read %.2f)" % (gb_8d / peak)
+                                 if shared_law else "SURVEY.md 8d byte model applies (gensim's per-pair law)"),
+                "frac_dram": (traffic / (k_ms / n_launch / 1e3) / 1e9 / peak) if traffic else None,   # measured DRAM
+                                                                              # bytes (ncu, same launch size) over the live kernel time
+                "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)", "peak_source": src,
+                "bound_note": "not HBM-bound: most rows are served by the 126 MB L2 (hit rate ~75 %); ncu shows issue slots "
+                              "~60 % busy and DRAM ~20 %: the kernel is bound by instruction issue and L2 row-transaction "
+                              "latency (DESIGN.md 3.4), so frac_model > frac_dram",
                 "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                 "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / n_launch,
                 ("carried_rows_per_launch" if block else "centres_per_launch"): centres / world / n_launch,
                 "ms_per_launch": k_ms / n_launch,
-                "GBps_at_7168B_per_pair": my_pairs_rank * BYTES_PER_PAIR / (k_ms / 1e3) / 1e9}
+                "GBps_at_7168B_per_pair": gb_8d}
         if tables is None:
             S, T, P = (float(cn[0]) / world, float(cn[1]) / world, float(cn[3]) / world)
             wbytes = 20 * S + 4 * T + 4 * P
@@ -387,8 +460,11 @@ def run_ours(a):
             T = P = 0.0
             wbytes = BYTES_PER_ALIAS_STEP * S
         w_gbs = wbytes / (walk_ms / 1e3) / 1e9
+        w_traffic, w_traffic_src = ncu_traffic("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed)
+                                               else "walk_%s_kernel" % a.walk_mode, wkey)
         roof_walk = {"kernel": ("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode), "bound": "hbm", "achieved": w_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": NCU_TRAFFIC.get("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode) if (a.scale == 22 and a.batch_walks == 1 << 19 and world == 1) else None,
+                     "unit": "GB/s", "frac": w_gbs / peak, "traffic": w_traffic, "traffic_source": w_traffic_src,
+                     "frac_dram": (w_traffic / (walk_ms / a.steps / 1e3) / 1e9 / peak) if w_traffic else None,
                      "algorithmic_bytes_per_launch": wbytes / a.steps,
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}
@@ -522,19 +598,26 @@ def run_reference(a):
         off = np.arange(nw + 1, dtype=np.int64) * a.walk_length
         _, _, pairs = oracle.sgns_train(tok, off, voc, dim=a.dim, window=a.window, negative=a.negative,
                                         workers=cores, rng_mode=0, seed=1, syn0=syn0, syn1neg=syn1)
-        return steps, pairs, t1
+        t2 = time.time()
+        # the same walks once more under the GPU arm's default law (one negative set per centre occurrence):
+        # like-for-like SGNS rate, reported beside the line's value (which is the reference's own per-pair law)
+        _, _, pairs_s = oracle.sgns_train(tok, off, voc, dim=a.dim, window=a.window, negative=a.negative,
+                                          workers=cores, rng_mode=2, seed=1, syn0=syn0, syn1neg=syn1)
+        shared["pairs"] += pairs_s; shared["s"] += time.time() - t2
+        return steps, pairs, t1, t2
 
+    shared = {"pairs": 0, "s": 0.0}
     for i in range(a.warmup):
         one_step(i)
-    t0 = time.time()
+    shared = {"pairs": 0, "s": 0.0}
     steps = pairs = 0
-    t_walk = 0.0
+    t_walk = dt = 0.0
     for i in range(a.warmup, a.warmup + a.steps):
         ts = time.time()
-        s, p, t1 = one_step(i)
+        s, p, t1, t2 = one_step(i)
         t_walk += t1 - ts
+        dt += t2 - ts                      # the timed step = walks + the reference's own (per-pair) SGNS law
         steps += s; pairs += p
-    dt = time.time() - t0
     val = pairs / dt
     sample = (f"{nw} walks per step ({steps} steps, {pairs} pairs in {dt:.1f} s; walk phase {t_walk:.1f} s), "
               f"on-the-fly walker + SGNS port, {cores} threads, full [V={voc.V},{a.dim}] tables")
@@ -546,6 +629,9 @@ def run_reference(a):
         "dtype": "f32 rows / int32 ids", "data": "synthetic", "config": config_of(a, n, g.nnz),
         "walk_steps_per_s": steps / max(t_walk, 1e-9), "sgns_pairs_per_s_kernel": pairs / max(dt - t_walk, 1e-9),
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "negative_law": "fresh set of 5 per (centre, context) pair (gensim's law, the reference's); the GPU arm's default "
+                        "shares one set per centre occurrence -- its per-pair kernel is in its line's other_negative_mode",
+        "sgns_pairs_per_s_shared_negative_law": shared["pairs"] / max(shared["s"], 1e-9),
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 

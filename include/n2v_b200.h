@@ -249,27 +249,30 @@ int n2v_sgns_train_sharded(const int32_t *tokens, const int64_t *sent_off, int64
  * context is in part b. Stream (part, b) touches only syn1neg part `part` and syn0 part b, so GPU
  * k trains stream (k, (k + e) % n_parts) in sub-step e and the syn0 parts travel round a ring: no
  * row is replicated, nothing is averaged.
- * Stream format, uint32 words: the pairs of one centre occurrence inside a stream are a GROUP =
- * {0x80000000 | centre local row, sentence index within this call, token position | pairs << 16}
- * followed by one word per pair (the context's local row); only a group's first word has bit 31 set.
+ * Stream format, uint32 words: the pairs of one centre occurrence inside a stream are a GROUP = 8
+ * header words {0x80000000 | centre local row, sentence index within this call, token position |
+ * pairs << 16, the centre's 5 negatives as local rows of `part`} followed by one word per pair (the
+ * context's local row); only a group's first word has bit 31 set.
  *   n2v_sgns_groups_count: offsets int64[n_parts * n_sent + 1], exclusive scan of the per-(stream,
  *       sentence) word counts in stream-major order: stream b = words [offsets[b * n_sent],
  *       offsets[(b + 1) * n_sent]); the last entry is the total.
  *   n2v_sgns_groups_fill: writes the words (order: stream, sentence, centre, context); words beyond
- *       capacity_words are dropped and counted in *overflow (device uint64).
+ *       capacity_words are dropped and counted in *overflow (device uint64). It also draws every
+ *       centre's negative set, once, and repeats it in the header of each stream the centre reaches:
+ *       Philox ctr (sent_id_base + sentence index, position / neg_group << 16 | 0xFFFF, epoch) ->
+ *       count^0.75 table, i.e. the very draws n2v_sgns_train makes for that centre (neg_group = 1),
+ *       each mapped to the word of the same local row in `part`.
  *   n2v_sgns_train_groups: trains the stream words[first_word, first_word + n_words) -- or, when
  *       dev_first / dev_end are given, [*dev_first, *dev_end) read on the device (two entries of
  *       `offsets`; no host round trip), clamped to capacity_words -- against (syn0 part of the
  *       stream's contexts, syn1neg part `part`). Every warp takes one contiguous range of whole
- *       groups. Negatives: ONE set of 5 per centre occurrence, Philox ctr (sent_id_base + sentence
- *       index, position << 16 | 0xFFFF, epoch) -> count^0.75 table, i.e. the very draws n2v_sgns_train
- *       makes for that centre, each mapped to the word of the same local row in `part`; a negative
+ *       groups. Negatives: the set in the group's header (ONE per centre occurrence); a negative
  *       equal to the centre is skipped, a set with a repeated row runs pair by pair with gensim's
- *       sequential semantics. neg_group = G > 1: the centres at G consecutive token positions of a
- *       sentence share one set (position / G in the counter). alpha follows the sentence's job
- *       (params->alpha0, min_alpha, total_examples, example_base, sent_per_job) as in n2v_sgns_train.
- *       Also uses params->V, dim (<= 128, % 4), negative (5), bucket_bits, seed, epoch, grid_warps,
- *       atomic_updates. pairs_out[0] += pairs, [1] += output rows carried in registers (one centre
+ *       sequential semantics. neg_group = G > 1 (the value given to n2v_sgns_groups_fill): the centres
+ *       at G consecutive token positions of a sentence carry the same set, which is then kept in
+ *       registers across them. alpha follows the sentence's job (params->alpha0, min_alpha,
+ *       total_examples, example_base, sent_per_job) as in n2v_sgns_train. Also uses params->V, dim
+ *       (<= 128, % 4), negative (5), grid_warps, atomic_updates. pairs_out[0] += pairs, [1] += output rows carried in registers (one centre
  *       row per group + 5 per negative set): algorithmic bytes = 1,024 * (pairs + carried rows). */
 size_t n2v_sgns_groups_workspace_bytes(int64_t n_sent, int32_t n_parts);
 int n2v_sgns_groups_count(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
@@ -279,11 +282,11 @@ int n2v_sgns_groups_count(const int32_t *tokens, const int64_t *sent_off, int64_
 int n2v_sgns_groups_fill(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
                          int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
                          const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
+                         const uint32_t *cum_table, const int32_t *bucket_lo, int32_t neg_group,
                          const int64_t *offsets, uint32_t *words, int64_t capacity_words,
                          unsigned long long *overflow, void *stream);
 int n2v_sgns_train_groups(const uint32_t *words, int64_t first_word, int64_t n_words,
                           const int64_t *dev_first, const int64_t *dev_end, int64_t capacity_words,
-                          int64_t sent_id_base, const uint32_t *cum_table, const int32_t *bucket_lo,
                           const n2v_sgns_params_t *params, int32_t neg_group, float *syn0_part,
                           float *syn1neg_part, int32_t part, int32_t n_parts,
                           unsigned long long *pairs_out, void *stream);

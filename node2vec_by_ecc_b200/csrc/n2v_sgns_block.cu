@@ -15,9 +15,12 @@
 //   n2v_sgns_train_groups           one stream against (syn0 part, syn1neg part)
 //
 // Stream format (uint32 words). The pairs of one centre occurrence that fall into a stream form a
-// GROUP: 3 header words {0x80000000 | centre local row, sentence index in the pool, token position |
-// pair count << 16} followed by one word per pair, the context's local row. Only the first header word
-// has bit 31 set, so any word offset can be re-synchronised by scanning for it.
+// GROUP: 8 header words {0x80000000 | centre local row, sentence index in the pool, token position |
+// pair count << 16, the 5 negatives of the centre as local rows of its part} followed by one word per
+// pair, the context's local row. Only the first header word has bit 31 set, so any word offset can be
+// re-synchronised by scanning for it. The negatives are drawn ONCE per centre occurrence, by the
+// expansion kernel, and repeated in the header of every stream the centre reaches: the training kernel
+// (whose groups hold ~2 pairs at 8 parts) runs no Philox rounds and no table search of its own.
 //
 // Law. Exactly the sentence-major shared-negative kernel's (n2v_sgns.cu v3), whatever n_parts is: ONE
 // negative set per centre occurrence, drawn from Philox (sentence id, position) -> count^0.75 table --
@@ -42,6 +45,7 @@ namespace n2v {
 constexpr int BLK_MAX_PARTS = 8;
 constexpr int BLK_FN = 5;
 constexpr uint32_t GROUP_FLAG = 0x80000000u;
+constexpr int GROUP_HDR = 8;             // header words of a group
 
 struct GroupsArgs {
     SgnsArgs a;
@@ -50,6 +54,7 @@ struct GroupsArgs {
     const int64_t *offsets;     // [n_parts][n_sent] exclusive (fill pass)
     uint32_t *words; int64_t capacity;
     unsigned long long *overflow;
+    const uint32_t *cum_table; const int32_t *bucket_lo; int32_t neg_group;     // fill pass: the centres' negative sets
 };
 
 // One warp per sentence: sub-sample + window shrink exactly as the sentence-major kernels
@@ -64,6 +69,7 @@ sgns_groups_kernel(GroupsArgs g)
     __shared__ long long s_cur[SGNS_BLOCK / 32][BLK_MAX_PARTS];      // next free word of every stream
     __shared__ long long s_hdr[SGNS_BLOCK / 32][BLK_MAX_PARTS];      // header of the current centre's group (-1: none yet)
     __shared__ int32_t s_cnt[SGNS_BLOCK / 32][BLK_MAX_PARTS];
+    __shared__ int32_t s_neg[SGNS_BLOCK / 32][BLK_FN];
     const SgnsArgs &a = g.a;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
@@ -96,6 +102,18 @@ sgns_groups_kernel(GroupsArgs g)
                 int32_t j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
                 int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 if (lane < BLK_MAX_PARTS) { s_hdr[wib][lane] = -1ll; s_cnt[wib][lane] = 0; }
+                if (FILL && lane < BLK_FN) {
+                    // lane n draws negative n of this centre: the sentence-major kernel's draw_centre (Philox ctr
+                    // (gs lo, gs hi, position key << 16 | 0xFFFF, epoch << 8 | 1 + n / 4)) -> count^0.75 table -> the
+                    // word of the same local row in this part; position key = position / neg_group
+                    const uint32_t poskey = g.neg_group > 1 ? (uint32_t)ws.pos[i] / (uint32_t)g.neg_group : (uint32_t)ws.pos[i];
+                    const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (poskey << 16) | 0xFFFFu,
+                                                    ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
+                    const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
+                    int32_t t = draw_negative(rr, g.cum_table, g.bucket_lo, a.p.V, a.p.bucket_bits) >> g.lg;
+                    if ((((int64_t)t << g.lg) | g.part) >= a.p.V) --t;
+                    s_neg[wib][lane] = t;
+                }
                 __syncwarp();
                 for (int32_t jb = j0; jb < kend; jb += 32) {
                     const int32_t j = jb + lane;
@@ -109,22 +127,24 @@ sgns_groups_kernel(GroupsArgs g)
                     __syncwarp();
                     if (valid && rank == 0) {
                         if (fresh) s_hdr[wib][b] = base;
-                        s_cur[wib][b] = base + (fresh ? 3 : 0) + __popc(peers);
+                        s_cur[wib][b] = base + (fresh ? GROUP_HDR : 0) + __popc(peers);
                         s_cnt[wib][b] += __popc(peers);
                     }
                     __syncwarp();
                     if (FILL && valid) {
-                        const long long o = base + (fresh ? 3 : 0) + rank;
+                        const long long o = base + (fresh ? GROUP_HDR : 0) + rank;
                         if (o < g.capacity) g.words[o] = (uint32_t)(x >> g.lg);
                         else if (rank == 0) atomicAdd(g.overflow, 1ull);
                     }
                 }
                 if (FILL && lane < g.n_parts && s_hdr[wib][lane] >= 0) {
                     const long long h = s_hdr[wib][lane];
-                    if (h + 2 < g.capacity) {
+                    if (h + GROUP_HDR - 1 < g.capacity) {
                         g.words[h] = GROUP_FLAG | (uint32_t)(centre >> g.lg);
                         g.words[h + 1] = (uint32_t)s;
                         g.words[h + 2] = (uint32_t)ws.pos[i] | ((uint32_t)s_cnt[wib][lane] << 16);
+#pragma unroll
+                        for (int d = 0; d < BLK_FN; ++d) g.words[h + 3 + d] = (uint32_t)s_neg[wib][d];
                     }
                 }
                 __syncwarp();
@@ -142,9 +162,7 @@ struct TrainGroupsArgs {
     int64_t first, end, capacity;              // the stream = words [first, end), clamped to capacity
     const int64_t *dev_first, *dev_end;        // optional device copies of first / end (no host round trip)
     float *syn0_part, *syn1neg_part;
-    const uint32_t *cum_table; const int32_t *bucket_lo;
     n2v_sgns_params_t p;
-    int64_t sent_id_base;
     int32_t part, lg, neg_group;
     unsigned long long *pairs_out;
 };
@@ -170,56 +188,42 @@ sgns_group_kernel(TrainGroupsArgs a)
     const int32_t dim = FULL ? 128 : a.p.dim;
     const bool on = FULL || (lane * 4 < dim);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
-    const uint32_t ep8 = a.p.epoch << 8;
     const int32_t G = a.neg_group;
     const RowsFlat rows{a.syn0_part, a.syn1neg_part, dim};
-    const uint32_t *const words = a.words;
     const int64_t first = a.dev_first ? *a.dev_first : a.first;
-    int64_t end = a.dev_end ? *a.dev_end : a.end;
-    if (end > a.capacity) end = a.capacity;
-    if (first >= end) return;
+    int64_t end64 = a.dev_end ? *a.dev_end : a.end;
+    if (end64 > a.capacity) end64 = a.capacity;
+    if (first >= end64) return;
+    // offsets below are relative to the stream's first word and 32-bit (the host checks the stream length)
+    const uint32_t *const words = a.words + first;
+    const uint32_t end = (uint32_t)(end64 - first);
     // this warp's contiguous range of the stream: the groups whose header lies in [lo, hi)
-    const int64_t per_warp = (end - first + n_warps - 1) / n_warps;
-    const int64_t lo = first + warp * per_warp;
-    const int64_t hi = lo + per_warp < end ? lo + per_warp : end;
-    if (lo >= hi) return;
-    int64_t p = lo;
+    const uint32_t per_warp = (uint32_t)(((uint64_t)end + (uint64_t)n_warps - 1) / (uint64_t)n_warps);
+    const uint64_t lo64 = (uint64_t)warp * per_warp;
+    if (lo64 >= end) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (end - lo > per_warp) ? lo + per_warp : end;
+    uint32_t p = lo;
     for (;;) {                                                 // first header at or after lo
         const uint32_t wv = (p + lane < end) ? __ldcs(words + p + lane) : 0u;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, (wv & GROUP_FLAG) != 0u);
         if (m) { p += __ffs(m) - 1; break; }
+        if (hi - p <= 32u) return;
         p += 32;
-        if (p >= hi) return;
     }
     if (p >= hi) return;
 
-    unsigned long long pairs = 0, carried = 0;
+    uint32_t pairs = 0, carried = 0;                           // per warp and launch: far below 2^32
     auto sigmoid_g = [&](float f, float label, float alpha) -> float {
         return (label - s_exp[(int)((f + (float)MAX_EXP) * (float)(EXP_TABLE_SIZE / MAX_EXP / 2))]) * alpha;
     };
-    // lane n (< 5) draws negative n of the set keyed (sentence, position key): the sentence-major kernel's
-    // draw_centre (Philox ctr (gs lo, gs hi, key << 16 | 0xFFFF, epoch << 8 | 1 + n / 4)), then the word of
-    // the same local row in this part
-    auto draw_set = [&](uint32_t s_in_pool, uint32_t poskey) -> int32_t {
-        int32_t t = -1;
-        if (lane < FN) {
-            const uint64_t gs = (uint64_t)(a.sent_id_base + (int64_t)s_in_pool);
-            const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (poskey << 16) | 0xFFFFu,
-                                            ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
-            const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
-            t = draw_negative(rr, a.cum_table, a.bucket_lo, a.p.V, a.p.bucket_bits) >> a.lg;
-            if ((((int64_t)t << a.lg) | a.part) >= a.p.V) --t;
-        }
-        return t;
-    };
-    auto load_tile = [&](int64_t q) -> uint32_t {             // header + first 29 contexts of the group at q
+    auto load_tile = [&](uint32_t q) -> uint32_t {            // header + first 24 contexts of the group at q
         return (q < hi && q + lane < end) ? __ldcs(words + q + lane) : 0u;
     };
     auto poskey_of = [&](uint32_t h2) -> uint32_t { return G > 1 ? (h2 & 0xFFFFu) / (uint32_t)G : (h2 & 0xFFFFu); };
 
     uint32_t tile = load_tile(p);
-    int64_t pn = p + 3 + (int64_t)(__shfl_sync(0xFFFFFFFFu, tile, 2) >> 16);
+    uint32_t pn = p + GROUP_HDR + (__shfl_sync(0xFFFFFFFFu, tile, 2) >> 16);
     uint32_t tile_n = load_tile(pn);
     // state of the carried negative set
     uint32_t set_s = 0xFFFFFFFFu, set_key = 0xFFFFFFFFu;
@@ -230,8 +234,6 @@ sgns_group_kernel(TrainGroupsArgs a)
     for (int d = 0; d <= FN; ++d) out[d] = zero4;
 #pragma unroll
     for (int d = 0; d < FN; ++d) tg[d] = 0;
-    int32_t t_cur = draw_set(__shfl_sync(0xFFFFFFFFu, tile, 1), poskey_of(__shfl_sync(0xFFFFFFFFu, tile, 2)));
-    int32_t t_lanes = t_cur;                                   // lane n holds negative n of the live set (fallback path)
     uint32_t alpha_s = 0xFFFFFFFFu; float alpha = 0.f;
     auto flush_set = [&]() {
         if (set_live && !set_dup) {
@@ -254,18 +256,26 @@ sgns_group_kernel(TrainGroupsArgs a)
         // the group after next: its tile is in flight during this group (its address needs tile_n's count)
         const uint32_t n1 = __shfl_sync(0xFFFFFFFFu, tile_n, 1), n2 = __shfl_sync(0xFFFFFFFFu, tile_n, 2);
         const bool have_next = pn < hi;
-        const int64_t pnn = pn + 3 + (int64_t)(n2 >> 16);
+        const uint32_t pnn = pn + GROUP_HDR + (n2 >> 16);
         const uint32_t tile_nn = have_next ? load_tile(pnn) : 0u;
         if (h1 != alpha_s) { alpha = job_alpha(a.p, (int64_t)h1); alpha_s = h1; }
         auto ctx_at = [&](int32_t j) -> int32_t {
-            return j < 29 ? (int32_t)__shfl_sync(0xFFFFFFFFu, tile, 3 + j) : (int32_t)__ldg(words + p + 3 + j);
+            return j < 32 - GROUP_HDR ? (int32_t)__shfl_sync(0xFFFFFFFFu, tile, GROUP_HDR + j)
+                                      : (int32_t)__ldg(words + p + GROUP_HDR + j);
         };
-        // ---- negative set of this group: the carried one is kept while the key is unchanged (G > 1)
-        if (!set_live || h1 != set_s || key != set_key) {
-            flush_set();
-            t_lanes = t_cur;
+        // ---- negative set of this group: the carried one is kept while the key is unchanged (G > 1) -- unless
+        // this centre IS one of the carried rows: its row must then be read after the set's pending updates
+        bool keep_set = set_live && h1 == set_s && key == set_key;
+        bool collide = false;                      // (only ever true when G > 1 carries a set across centres)
+        if (keep_set && !set_dup) {
 #pragma unroll
-            for (int d = 0; d < FN; ++d) tg[d] = __shfl_sync(0xFFFFFFFFu, t_cur, d);
+            for (int d = 0; d < FN; ++d) collide |= (tg[d] == centre);
+            keep_set = !collide;
+        }
+        if (!keep_set) {
+            flush_set();
+#pragma unroll
+            for (int d = 0; d < FN; ++d) tg[d] = (int32_t)__shfl_sync(0xFFFFFFFFu, tile, 3 + d);
             set_dup = false;
 #pragma unroll
             for (int d1 = 0; d1 < FN; ++d1)
@@ -276,13 +286,11 @@ sgns_group_kernel(TrainGroupsArgs a)
                 for (int d = 0; d < FN; ++d) out[d + 1] = on ? ldcg4(rows.r1(tg[d]), lane) : zero4;
 #pragma unroll
                 for (int d = 1; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
-                carried += FN;
+                carried += (uint32_t)FN;
             }
             set_live = true; set_s = h1; set_key = key;
         }
-        // the next group's set, drawn while this group's rows arrive (only if it differs)
         const bool next_new = have_next && (n1 != set_s || poskey_of(n2) != set_key);
-        const int32_t t_nxt = next_new ? draw_set(n1, poskey_of(n2)) : t_cur;
         if (!set_dup) {
             uint32_t skipmask = 0xC0u;                 // padding targets 6, 7
 #pragma unroll
@@ -299,7 +307,7 @@ sgns_group_kernel(TrainGroupsArgs a)
                 if (next_new) {
 #pragma unroll
                     for (int d = 0; d < FN; ++d) {
-                        const int32_t tn = __shfl_sync(0xFFFFFFFFu, t_nxt, d);
+                        const int32_t tn = (int32_t)__shfl_sync(0xFFFFFFFFu, tile_n, 3 + d);
                         if (on) prefetch_row_l2(rows.r1(tn), lane);
                     }
                 }
@@ -354,20 +362,28 @@ sgns_group_kernel(TrainGroupsArgs a)
                 add_row<ATOMIC>(rows.r1(centre), lane,
                                 make_float4(out[0].x - og.x, out[0].y - og.y, out[0].z - og.z, out[0].w - og.w), out[0], on);
             }
+            if (G > 1) {                               // a carried negative that IS this centre is stale now: drop the set
+                bool again = false;
+#pragma unroll
+                for (int d = 0; d < FN; ++d) again |= (tg[d] == centre);
+                if (again) flush_set();
+            }
         } else {
             // repeated row in the set: uncarried sequential form (every target re-read per pair), gensim's
             // semantics for a repeated draw -- the sentence-major kernel's fallback
             const bool act1[1] = {on};
+            const int32_t t_lanes = lane == 0 ? tg[0] : lane == 1 ? tg[1] : lane == 2 ? tg[2] : lane == 3 ? tg[3] : tg[4];
             for (int32_t j = 0; j < cnt; ++j)
                 train_pair<1, ATOMIC>(rows, dim, centre, ctx_at(j), t_lanes, FN, alpha, act1, s_exp, lane);
         }
-        pairs += (unsigned long long)cnt;
-        t_cur = t_nxt;
+        pairs += (uint32_t)cnt;
         p = pn; pn = pnn;
         tile = tile_n; tile_n = tile_nn;
     }
     flush_set();
-    if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, carried); }
+    if (lane == 0 && a.pairs_out && pairs) {
+        atomicAdd(a.pairs_out, (unsigned long long)pairs); atomicAdd(a.pairs_out + 1, (unsigned long long)carried);
+    }
 }
 
 static inline size_t blk_align(size_t x, size_t al = 256) { return (x + al - 1) / al * al; }
@@ -443,6 +459,7 @@ extern "C" int n2v_sgns_groups_count(const int32_t *tokens, const int64_t *sent_
 extern "C" int n2v_sgns_groups_fill(const int32_t *tokens, const int64_t *sent_off, int64_t n_sent, int32_t stride,
                                     int64_t sent_id_base, const int32_t *vocab_of_id, const uint32_t *keep_thr,
                                     const n2v_sgns_params_t *params, int32_t part, int32_t n_parts,
+                                    const uint32_t *cum_table, const int32_t *bucket_lo, int32_t neg_group,
                                     const int64_t *offsets, uint32_t *words, int64_t capacity_words,
                                     unsigned long long *overflow, void *stream_)
 {
@@ -451,8 +468,12 @@ extern "C" int n2v_sgns_groups_fill(const int32_t *tokens, const int64_t *sent_o
     int rc = groups_args(g, tokens, sent_off, n_sent, stride, sent_id_base, vocab_of_id, keep_thr, params, part, n_parts);
     if (rc != N2V_OK) return rc;
     N2V_REQUIRE(offsets && words && overflow && capacity_words >= 0, "offsets / words / overflow is NULL");
+    N2V_REQUIRE(cum_table && bucket_lo, "cum_table / bucket_lo is NULL");
+    N2V_REQUIRE(neg_group >= 1 && neg_group <= 256, "neg_group must be in [1, 256]");
+    N2V_REQUIRE(params->V >= n_parts && params->bucket_bits >= 1 && params->bucket_bits <= 24, "bad vocabulary parameters");
     if (n_sent == 0) return N2V_OK;
     g.offsets = offsets; g.words = words; g.capacity = capacity_words; g.overflow = overflow;
+    g.cum_table = cum_table; g.bucket_lo = bucket_lo; g.neg_group = neg_group;
     int sms = sm_count();
     if (sms <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
     int64_t blocks = (n_sent + SGNS_BLOCK / 32 - 1) / (SGNS_BLOCK / 32);
@@ -464,7 +485,6 @@ extern "C" int n2v_sgns_groups_fill(const int32_t *tokens, const int64_t *sent_o
 
 extern "C" int n2v_sgns_train_groups(const uint32_t *words, int64_t first_word, int64_t n_words,
                                      const int64_t *dev_first, const int64_t *dev_end, int64_t capacity_words,
-                                     int64_t sent_id_base, const uint32_t *cum_table, const int32_t *bucket_lo,
                                      const n2v_sgns_params_t *params, int32_t neg_group, float *syn0_part,
                                      float *syn1neg_part, int32_t part, int32_t n_parts,
                                      unsigned long long *pairs_out, void *stream_)
@@ -472,9 +492,10 @@ extern "C" int n2v_sgns_train_groups(const uint32_t *words, int64_t first_word, 
     cudaStream_t stream = (cudaStream_t)stream_;
     N2V_REQUIRE(params, "params is NULL");
     N2V_REQUIRE(first_word >= 0 && n_words >= 0 && capacity_words >= 0, "negative size");
+    N2V_REQUIRE(n_words < 4294967296ll - 64, "a stream holds at most 2^32 words per launch");
     N2V_REQUIRE((dev_first == nullptr) == (dev_end == nullptr), "dev_first and dev_end go together");
     if (!dev_first && n_words == 0) return N2V_OK;
-    N2V_REQUIRE(words && cum_table && bucket_lo && syn0_part && syn1neg_part, "NULL buffer");
+    N2V_REQUIRE(words && syn0_part && syn1neg_part, "NULL buffer");
     const int lg = log2_parts(n_parts);
     N2V_REQUIRE(lg >= 0 && part >= 0 && part < n_parts, "n_parts must be 1, 2, 4 or 8 and 0 <= part < n_parts");
     const n2v_sgns_params_t &p = *params;
@@ -482,17 +503,16 @@ extern "C" int n2v_sgns_train_groups(const uint32_t *words, int64_t first_word, 
     N2V_REQUIRE(p.dim >= 4 && p.dim <= 128 && p.dim % 4 == 0, "block kernel: dim must be a multiple of 4, <= 128");
     N2V_REQUIRE(p.negative == BLK_FN, "block kernel: negative must be 5");
     N2V_REQUIRE(neg_group >= 1 && neg_group <= 256, "neg_group must be in [1, 256]");
-    N2V_REQUIRE(p.bucket_bits >= 1 && p.bucket_bits <= 24, "bucket_bits out of range");
     N2V_REQUIRE(p.grid_warps >= 1 && p.total_examples >= 1 && p.sent_per_job >= 1, "bad schedule");
     if (sm_count() <= 0) { set_error("no CUDA device"); return N2V_ECUDA; }
     TrainGroupsArgs a;
     memset(&a, 0, sizeof(a));
     a.words = words; a.first = first_word; a.end = first_word + n_words; a.capacity = capacity_words;
     a.dev_first = dev_first; a.dev_end = dev_end;
-    a.syn0_part = syn0_part; a.syn1neg_part = syn1neg_part; a.cum_table = cum_table; a.bucket_lo = bucket_lo;
-    a.p = p; a.sent_id_base = sent_id_base; a.part = part; a.lg = lg; a.neg_group = neg_group; a.pairs_out = pairs_out;
-    if (!dev_first) {                      // no more warps than groups could exist (a group is >= 4 words)
-        const int64_t most = (n_words + 3) / 4;
+    a.syn0_part = syn0_part; a.syn1neg_part = syn1neg_part;
+    a.p = p; a.part = part; a.lg = lg; a.neg_group = neg_group; a.pairs_out = pairs_out;
+    if (!dev_first) {                      // no more warps than groups could exist (a group is >= 9 words)
+        const int64_t most = (n_words + GROUP_HDR) / (GROUP_HDR + 1);
         if (most < a.p.grid_warps) a.p.grid_warps = (int32_t)(most > 0 ? most : 1);
     }
     const int wpb = SGNS_BLOCK / 32;

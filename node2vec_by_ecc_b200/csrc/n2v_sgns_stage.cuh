@@ -132,13 +132,42 @@ __device__ __forceinline__ void prefetch_row_l2(const float *row, int lane)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4 *>(row) + lane));
 }
+// Packed fp32 pairs (sm_100a FFMA2 / FMUL2: one issue slot for two fused multiply-adds). A float4 from a
+// 128-bit load sits in an aligned register quad, so (x, y) and (z, w) are register pairs and the
+// mov.b64 packs below cost nothing. Each half is an ordinary fma.rn, so the per-element results are those
+// of scalar code; only the dot product's summation order differs: (x.x*y.x + x.z*y.z) + (x.y*y.y + x.w*y.w).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b)
+{
+    f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 __device__ __forceinline__ float dot4(const float4 &x, const float4 &y)
 {
-    return x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    f32x2_t t = mul2(pack2(x.x, x.y), pack2(y.x, y.y));
+    t = fma2(pack2(x.z, x.w), pack2(y.z, y.w), t);
+    float a, b;
+    unpack2(t, a, b);
+    return a + b;
 }
 __device__ __forceinline__ void axpy4(float4 &acc, float g, const float4 &x)
 {
-    acc.x += g * x.x; acc.y += g * x.y; acc.z += g * x.z; acc.w += g * x.w;
+    const f32x2_t gg = pack2(g, g);
+    const f32x2_t lo = fma2(gg, pack2(x.x, x.y), pack2(acc.x, acc.y));
+    const f32x2_t hi = fma2(gg, pack2(x.z, x.w), pack2(acc.z, acc.w));
+    unpack2(lo, acc.x, acc.y);
+    unpack2(hi, acc.z, acc.w);
 }
 template <bool ATOMIC>
 __device__ __forceinline__ void add_row(float *row, int lane, const float4 &delta, const float4 &updated, bool on)

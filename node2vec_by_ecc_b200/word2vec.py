@@ -166,7 +166,7 @@ class SgnsTrainer:
     bench.py drives this class directly on device-resident walk buffers."""
 
     def __init__(self, counts_by_id: torch.Tensor, dim=128, window=10, negative=5, sample=1e-3, seed=1,
-                 alpha=0.025, min_alpha=1e-4, min_count=0, batch_words=10000):
+                 alpha=0.025, min_alpha=1e-4, min_count=0, batch_words=10000, first_seen=None):
         dev = require_cuda()
         L = lib()
         counts = counts_by_id.to(device=dev, dtype=torch.int64).contiguous()
@@ -174,9 +174,15 @@ class SgnsTrainer:
         self.dim, self.window, self.negative, self.sample = int(dim), int(window), int(negative), float(sample)
         self.seed, self.alpha, self.min_alpha, self.batch_words = int(seed), float(alpha), float(min_alpha), int(batch_words)
         keep = counts >= max(int(min_count), 1)
-        # count descending, ties by id: ids are first-seen order for generic corpora and compact node
-        # ids for walk corpora (gensim's tie order is dict order -- unspecified in Python 2)
-        order = torch.sort(torch.where(keep, counts, torch.zeros_like(counts)), descending=True, stable=True).indices
+        # count descending, ties by first appearance in the corpus (`first_seen`: position of the id's first
+        # token; ids of generic corpora already are in first-seen order) -- gensim's own tie order is dict
+        # order, unspecified in Python 2; first-seen makes every ingest path of one corpus agree
+        kept = torch.where(keep, counts, torch.zeros_like(counts))
+        if first_seen is None:
+            order = torch.sort(kept, descending=True, stable=True).indices
+        else:
+            by_first = torch.argsort(first_seen.to(dev), stable=True)
+            order = by_first[torch.sort(kept[by_first], descending=True, stable=True).indices]
         V = int(keep.sum().item())
         if V == 0:
             raise RuntimeError("you must first build vocabulary before training the model")
@@ -432,8 +438,9 @@ class BlockSgnsTrainer(SgnsTrainer):
             if b.get("cap", -1) < (total if exact_bounds else int(total * 1.5)):
                 b["cap"] = want
                 b["words"] = torch.empty(want, dtype=torch.int32, device=dev)
-        check(lib().n2v_sgns_groups_fill(*head, ptr(b["offsets"]), ptr(b["words"]), C.c_int64(b["cap"]),
-                                         ptr(b["overflow"]), stream()))
+        check(lib().n2v_sgns_groups_fill(*head, ptr(self.cum_table), ptr(self.bucket_lo), C.c_int32(self.neg_group),
+                                         ptr(b["offsets"]), ptr(b["words"]), C.c_int64(b["cap"]), ptr(b["overflow"]),
+                                         stream()))
         return b["words"], bounds
 
     def train_bucket(self, part, bucket, syn0_part, P, n_sent, sent_id_base, bounds=None):
@@ -448,8 +455,7 @@ class BlockSgnsTrainer(SgnsTrainer):
             base = b["offsets"].data_ptr()
             d0, d1 = C.c_void_p(base + 8 * bucket * n_sent), C.c_void_p(base + 8 * (bucket + 1) * n_sent)
         check(lib().n2v_sgns_train_groups(ptr(b["words"]), C.c_int64(first), C.c_int64(n), d0, d1, C.c_int64(b["cap"]),
-                                          C.c_int64(sent_id_base), ptr(self.cum_table), ptr(self.bucket_lo), C.byref(P),
-                                          C.c_int32(self.neg_group), ptr(syn0_part), ptr(self.parts1[part]),
+                                          C.byref(P), C.c_int32(self.neg_group), ptr(syn0_part), ptr(self.parts1[part]),
                                           C.c_int32(part), C.c_int32(self.n_parts), ptr(self.pairs), stream()))
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
@@ -677,6 +683,16 @@ class Word2Vec:
         counts = torch.zeros(max(n_ids, 1), dtype=torch.int64, device=dev)
         check(lib().n2v_vocab_count(ptr(tok), C.c_int64(tok.numel()), C.c_int32(n_ids), ptr(counts), stream()))
         shard = getattr(self, "_shard", None)
+        first_seen = None
+        if off is None and stride > 0:            # a walk buffer: token ids are node ids, not first-seen ranks
+            flat = tok.reshape(-1)
+            pos = torch.nonzero(flat >= 0).reshape(-1)
+            ids = flat[pos].to(torch.int64)
+            if shard is not None:                 # positions in the whole corpus: this rank's share starts here
+                pos = pos + int(shard[0]) * (-(-int(shard[2]) // int(shard[1]))) * stride
+            first_seen = torch.full((max(n_ids, 1),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+            first_seen.scatter_reduce_(0, ids, pos, reduce="amin")
+            del flat, pos, ids
         if shard is not None:
             # one rank's share of a corpus simulated by `world` processes: global counts, tables cut into
             # `world` row sets, block-partitioned training over an NCCL ring (BlockSgnsTrainer)
@@ -684,16 +700,19 @@ class Word2Vec:
             if off is not None or self.vector_size > 128 or self.vector_size % 4 or self.negative != 5:
                 raise NotImplementedError("multi-GPU training needs a walk corpus, size <= 128 (multiple of 4), negative = 5")
             D.sum_counts(counts)
+            import torch.distributed as tdist
+            tdist.all_reduce(first_seen, op=tdist.ReduceOp.MIN)
             self.corpus_count = int(shard[2])
             self.trainer = T = BlockSgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
                                                 negative=self.negative, sample=self.sample, seed=self.seed,
                                                 alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
-                                                batch_words=self.batch_words)
+                                                batch_words=self.batch_words, first_seen=first_seen[:n_ids])
         else:
             self.trainer = T = SgnsTrainer(counts[:n_ids], dim=self.vector_size, window=self.window,
                                            negative=self.negative, sample=self.sample, seed=self.seed,
                                            alpha=self.alpha, min_alpha=self.min_alpha, min_count=self.min_count,
-                                           batch_words=self.batch_words)
+                                           batch_words=self.batch_words,
+                                           first_seen=None if first_seen is None else first_seen[:n_ids])
         # host-side vocabulary objects (what emb.vocab / index2word expose)
         order_h, vc_h = T.order.cpu().numpy(), T.counts.cpu().numpy()
         kt_h = T.keep_thr.cpu().numpy().view(np.uint32)
@@ -719,8 +738,8 @@ class Word2Vec:
                 T.train(tok[p0:p0 + n].contiguous(), None, n, stride, total_examples=max(1, per * world * epochs),
                         example_base=(ep * per + p0) * world, sent_id_base=(ep * per + p0) * world, epoch=ep,
                         sent_per_job=int(self.batch_words // mean_len), grid_warps=self.hogwild_warps,
-                        alpha=start_alpha, min_alpha=end_alpha)
-        T.check_overflow()
+                        alpha=start_alpha, min_alpha=end_alpha, exact_bounds=False)
+        self._overflow_check = T.check_overflow           # read with the pair count (no device sync per call)
         import torch.distributed as tdist
         mine = T.pairs[0] - before
         tdist.all_reduce(mine)
@@ -794,4 +813,7 @@ class Word2Vec:
         if getattr(self, "_pairs_pending", None) is not None:
             self._pairs_done += int(self._pairs_pending.item())
             self._pairs_pending = None
+        if getattr(self, "_overflow_check", None) is not None:
+            self._overflow_check()
+            self._overflow_check = None
         return self._pairs_done

@@ -291,10 +291,10 @@ def vocab_from_counts(counts_by_id, sample: float = 1e-3) -> Vocab:
 
 # ---- block-partitioned SGNS (csrc/n2v_sgns_block.cu) ---------------------------------------------
 def sgns_make_groups(tok_idx, sent_off, vocab: Vocab, part: int, n_parts: int, window=10, seed=1, epoch=0,
-                     sent_id_base=0, subsample=True):
+                     sent_id_base=0, subsample=True, neg_group=1):
     """-> list of n_parts uint32[n_b] word streams: the pairs whose centre is in `part`, stream b =
     context in part b, grouped per centre occurrence: {0x80000000 | centre local row, sentence index,
-    position | pairs << 16}, then the context local rows."""
+    position | pairs << 16, the centre's 5 negatives (local rows of `part`)}, then the context local rows."""
     tok = np.ascontiguousarray(tok_idx, dtype=np.int32).ravel()
     off = np.ascontiguousarray(sent_off, dtype=np.int64)
     lg = int(n_parts).bit_length() - 1
@@ -302,7 +302,8 @@ def sgns_make_groups(tok_idx, sent_off, vocab: Vocab, part: int, n_parts: int, w
     si = _p(vocab.sample_int, C.c_uint64) if subsample else None
     lens = np.zeros(n_parts, dtype=np.int64)
     args = (_p(tok, C.c_int32), _p(off, C.c_int64), C.c_int64(off.shape[0] - 1), C.c_int64(sent_id_base),
-            C.c_int32(window), si, C.c_uint64(seed), C.c_uint32(epoch), C.c_int32(part), C.c_int32(lg))
+            C.c_int32(window), si, C.c_uint64(seed), C.c_uint32(epoch), C.c_int32(part), C.c_int32(lg),
+            C.c_int32(vocab.V), _p(vocab.cum_table, C.c_uint32), C.c_int32(neg_group))
     assert lib().sgns_oracle_make_groups(*args, _p(lens, C.c_int64), None, None) == 0
     offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     words = np.zeros(max(int(offs[-1]), 1), dtype=np.uint32)
@@ -310,21 +311,17 @@ def sgns_make_groups(tok_idx, sent_off, vocab: Vocab, part: int, n_parts: int, w
     return [words[offs[b]:offs[b + 1]] for b in range(n_parts)]
 
 
-def sgns_train_groups(words, syn0_part, syn1_part, part: int, n_parts: int, vocab: Vocab, *, alpha=0.025,
-                      min_alpha=1e-4, total_examples=1, example_base=0, sent_per_job=1, sent_id_base=0,
-                      neg_group=1, seed=1, epoch=0) -> int:
+def sgns_train_groups(words, syn0_part, syn1_part, *, alpha=0.025, min_alpha=1e-4, total_examples=1,
+                      example_base=0, sent_per_job=1) -> int:
     """one stream against (syn0 part, syn1neg part `part`), in place; returns the pairs trained"""
     wd = np.ascontiguousarray(words, dtype=np.uint32)
     assert syn0_part.dtype == np.float32 and syn1_part.dtype == np.float32
     assert syn0_part.flags.c_contiguous and syn1_part.flags.c_contiguous
-    lg = int(n_parts).bit_length() - 1
     pairs = C.c_int64(0)
     rc = lib().sgns_oracle_train_groups(
         _p(wd, C.c_uint32), C.c_int64(wd.shape[0]), _p(syn0_part, C.c_float), _p(syn1_part, C.c_float),
-        C.c_int32(part), C.c_int32(lg), C.c_int32(vocab.V), C.c_int32(syn0_part.shape[1]),
-        _p(vocab.cum_table, C.c_uint32), C.c_float(alpha), C.c_float(min_alpha), C.c_int64(total_examples),
-        C.c_int64(example_base), C.c_int64(sent_per_job), C.c_int64(sent_id_base), C.c_int32(neg_group),
-        C.c_uint64(seed), C.c_uint32(epoch), C.byref(pairs))
+        C.c_int32(syn0_part.shape[1]), C.c_float(alpha), C.c_float(min_alpha), C.c_int64(total_examples),
+        C.c_int64(example_base), C.c_int64(sent_per_job), C.byref(pairs))
     assert rc == 0, rc
     return int(pairs.value)
 
@@ -336,15 +333,14 @@ def sgns_block_pool(tok_idx, sent_off, vocab: Vocab, parts0, parts1, *, window=1
     GPU k trains stream (k, (k + e) % n) against syn1neg part k and syn0 part (k + e) % n.
     parts0 / parts1: lists of float32[rows_k, dim] (updated in place). Returns the pair count."""
     n = len(parts0)
-    streams = [sgns_make_groups(tok_idx, sent_off, vocab, k, n, window, seed, epoch, sent_id_base, subsample)
+    streams = [sgns_make_groups(tok_idx, sent_off, vocab, k, n, window, seed, epoch, sent_id_base, subsample, neg_group)
                for k in range(n)]
     pairs = 0
     for e in range(n):
         for k in range(n):
             b = (k + e) % n
             if len(streams[k][b]):
-                pairs += sgns_train_groups(streams[k][b], parts0[b], parts1[k], k, n, vocab, alpha=alpha,
-                                           min_alpha=min_alpha, total_examples=total_examples,
-                                           example_base=example_base, sent_per_job=sent_per_job,
-                                           sent_id_base=sent_id_base, neg_group=neg_group, seed=seed, epoch=epoch)
+                pairs += sgns_train_groups(streams[k][b], parts0[b], parts1[k], alpha=alpha, min_alpha=min_alpha,
+                                           total_examples=total_examples, example_base=example_base,
+                                           sent_per_job=sent_per_job)
     return pairs

@@ -387,14 +387,19 @@ int sgns_oracle_train(const int32_t *tok, const int64_t *sent_off, int64_t n_sen
  * sgns_oracle_make_groups: the (centre, context) pairs of the sentences whose centre lies in `part`,
  * sub-sampling and window shrink addressed by Philox exactly as rng_mode bit 0 above, written as
  * n_parts streams (stream b = context in part b) in the order sentence, centre, context. The pairs
- * of one centre occurrence inside a stream form a group: {0x80000000 | centre local row, sentence
- * index, position | pairs << 16}, then one word per pair (context local row). Two calls: words ==
- * NULL counts (stream_len[b], in words), then fill with stream_off[b] = start of stream b. */
+ * of one centre occurrence inside a stream form a group: 8 header words {0x80000000 | centre local
+ * row, sentence index, position | pairs << 16, the centre's 5 negatives}, then one word per pair
+ * (context local row). The negatives are rng_mode 3's draws for that centre (Philox ctr (sentence id,
+ * position / G << 16 | 0xFFFF, epoch << 8 | 1 + n / 4) -> bisect_left(cum_table, r % cum[-1])), each
+ * mapped to the word of the same local row in `part`. Two calls: words == NULL counts (stream_len[b],
+ * in words), then fill with stream_off[b] = start of stream b. */
 int sgns_oracle_make_groups(const int32_t *tok, const int64_t *sent_off, int64_t n_sent, int64_t sent_id_base,
                             int32_t window, const uint64_t *sample_int, uint64_t seed, uint32_t epoch,
-                            int32_t part, int32_t lg, int64_t *stream_len, const int64_t *stream_off,
-                            uint32_t *words)
+                            int32_t part, int32_t lg, int32_t V, const uint32_t *cum_table, int32_t neg_group,
+                            int64_t *stream_len, const int64_t *stream_off, uint32_t *words)
 {
+    enum { FN = 5, HDR = 8 };
+    const uint32_t cum_last = cum_table[V - 1];
     const int32_t n_parts = 1 << lg, mask = n_parts - 1;
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
     int32_t *red = (int32_t *)malloc(sizeof(int32_t) * MAX_SENTENCE_LEN);
@@ -421,17 +426,27 @@ int sgns_oracle_make_groups(const int32_t *tok, const int64_t *sent_off, int64_t
             for (; j < k; ++j) {
                 if (j == i) continue;
                 const int32_t b = idx[j] & mask;
-                if (hdr[b] < 0) { hdr[b] = cur[b]; cur[b] += 3; }
+                if (hdr[b] < 0) { hdr[b] = cur[b]; cur[b] += HDR; }
                 if (words) words[cur[b]] = (uint32_t)(idx[j] >> lg);
                 ++cur[b]; ++cnt[b];
             }
-            if (words)
+            if (words) {
+                uint32_t tg[FN], rr[4] = {0, 0, 0, 0};
+                const uint32_t poskey = neg_group > 1 ? (uint32_t)pos[i] / (uint32_t)neg_group : (uint32_t)pos[i];
+                for (int32_t n2 = 0; n2 < FN; ++n2) {
+                    if ((n2 & 3) == 0) philox_words(seed, gs, (poskey << 16) | 0xFFFFu, (epoch << 8) | (uint32_t)(1 + (n2 >> 2)), rr);
+                    int32_t t = bisect_left_u32(cum_table, V, rr[n2 & 3] % cum_last) >> lg;
+                    if ((((int64_t)t << lg) | part) >= V) --t;
+                    tg[n2] = (uint32_t)t;
+                }
                 for (int32_t b = 0; b < n_parts; ++b)
                     if (hdr[b] >= 0) {
                         words[hdr[b]] = 0x80000000u | (uint32_t)(idx[i] >> lg);
                         words[hdr[b] + 1] = (uint32_t)s;
                         words[hdr[b] + 2] = (uint32_t)pos[i] | ((uint32_t)cnt[b] << 16);
+                        for (int32_t d = 0; d < FN; ++d) words[hdr[b] + 3 + d] = tg[d];
                     }
+            }
         }
     }
     if (!words) for (int32_t b = 0; b < n_parts; ++b) stream_len[b] = cur[b];
@@ -440,51 +455,37 @@ int sgns_oracle_make_groups(const int32_t *tok, const int64_t *sent_off, int64_t
 }
 
 /* sgns_oracle_train_groups: one stream against (syn0 part, syn1neg part `part`), group by group in
- * stream order. The law is rng_mode 3 above (Philox + one negative set per centre occurrence) with
- * every draw mapped to the word of the same local row in `part`: ctr = (sentence id, position / G <<
- * 16 | 0xFFFF, epoch << 8 | 1 + n / 4); alpha = the sentence's job alpha (jobs of sent_per_job
- * sentences, as the device's job_alpha). Pairs run through fast_sentence_sg_neg's arithmetic in
- * order, updates immediate -- which is what the device's carried registers + one reduction per row
- * compute when one warp runs alone. */
+ * stream order: the centre's negatives come from the group header, alpha = the sentence's job alpha
+ * (jobs of sent_per_job sentences, as the device's job_alpha). Pairs run through
+ * fast_sentence_sg_neg's arithmetic in order, updates immediate -- which is what the device's carried
+ * registers + one reduction per row compute when one warp runs alone. */
 int sgns_oracle_train_groups(const uint32_t *words, int64_t n_words, float *syn0_part, float *syn1_part,
-                             int32_t part, int32_t lg, int32_t V, int32_t dim, const uint32_t *cum_table,
-                             float alpha0, float min_alpha, int64_t total_examples, int64_t example_base,
-                             int64_t sent_per_job, int64_t sent_id_base, int32_t neg_group, uint64_t seed,
-                             uint32_t epoch, int64_t *pairs_out)
+                             int32_t dim, float alpha0, float min_alpha, int64_t total_examples,
+                             int64_t example_base, int64_t sent_per_job, int64_t *pairs_out)
 {
     pthread_once(&exp_once, build_exp_table);
-    enum { FN = 5 };
+    enum { FN = 5, HDR = 8 };
     float *work = (float *)malloc(sizeof(float) * (size_t)dim);
     if (!work) return -1;
-    const uint32_t cum_last = cum_table[V - 1];
     int64_t pairs = 0, p = 0;
     while (p < n_words) {
         if (!(words[p] & 0x80000000u)) { free(work); return -2; }
         const int32_t centre = (int32_t)(words[p] & 0x7FFFFFFFu);
-        const uint32_t s = words[p + 1], pos = words[p + 2] & 0xFFFFu;
+        const uint32_t s = words[p + 1];
         const int32_t cnt = (int32_t)(words[p + 2] >> 16);
-        const uint64_t gs = (uint64_t)(sent_id_base + (int64_t)s);
-        const uint32_t poskey = neg_group > 1 ? pos / (uint32_t)neg_group : pos;
-        int32_t tg[FN];
-        uint32_t rr[4] = {0, 0, 0, 0};
-        for (int32_t n = 0; n < FN; ++n) {
-            if ((n & 3) == 0) philox_words(seed, gs, (poskey << 16) | 0xFFFFu, (epoch << 8) | (uint32_t)(1 + (n >> 2)), rr);
-            int32_t t = bisect_left_u32(cum_table, V, rr[n & 3] % cum_last) >> lg;
-            if ((((int64_t)t << lg) | part) >= V) --t;
-            tg[n] = t;
-        }
+        const uint32_t *tg = words + p + 3;
         const int64_t ex = example_base + (int64_t)s;
         const int64_t job_first = ex - ex % sent_per_job;
         const double prog = (double)job_first / (double)total_examples;
         const double al = (double)alpha0 - ((double)alpha0 - (double)min_alpha) * prog;
         const float alpha = (float)(al > (double)min_alpha ? al : (double)min_alpha);
         for (int32_t j = 0; j < cnt; ++j) {
-            float *row1 = syn0_part + (int64_t)words[p + 3 + j] * dim;
+            float *row1 = syn0_part + (int64_t)words[p + HDR + j] * dim;
             memset(work, 0, sizeof(float) * (size_t)dim);
             for (int32_t k = 0; k <= FN; ++k) {
                 int32_t target; float label;
                 if (k == 0) { target = centre; label = 1.0f; }
-                else { target = tg[k - 1]; if (target == centre) continue; label = 0.0f; }
+                else { target = (int32_t)tg[k - 1]; if (target == centre) continue; label = 0.0f; }
                 float *row2 = syn1_part + (int64_t)target * dim;
                 float f = 0.0f;
                 for (int32_t i = 0; i < dim; ++i) f += row1[i] * row2[i];
@@ -497,7 +498,7 @@ int sgns_oracle_train_groups(const uint32_t *words, int64_t n_words, float *syn0
             for (int32_t i = 0; i < dim; ++i) row1[i] += work[i];
             ++pairs;
         }
-        p += 3 + cnt;
+        p += HDR + cnt;
     }
     if (pairs_out) *pairs_out = pairs;
     free(work);

@@ -229,9 +229,9 @@ def parse_groups(words):
     while p < len(words):
         assert words[p] & 0x80000000
         c, s, pos, cnt = int(words[p] & 0x7FFFFFFF), int(words[p + 1]), int(words[p + 2] & 0xFFFF), int(words[p + 2] >> 16)
-        assert cnt >= 1 and not (words[p + 3: p + 3 + cnt] & 0x80000000).any()
-        out += [(c, int(x), s, pos) for x in words[p + 3: p + 3 + cnt]]
-        p += 3 + cnt
+        assert cnt >= 1 and not (words[p + 1: p + 8 + cnt] & 0x80000000).any()
+        out += [(c, int(x), s, pos) for x in words[p + 8: p + 8 + cnt]]
+        p += 8 + cnt
     return np.asarray(out, dtype=np.int64).reshape(-1, 4)
 
 

@@ -97,8 +97,8 @@ def test_argument_guards_of_the_block_and_packed_entry_points():
     P.dim = 50
     words = torch.zeros(16, dtype=torch.int32, device="cuda")
     with pytest.raises(N2VError, match="multiple of 4"):
-        check(lib().n2v_sgns_train_groups(ptr(words), C.c_int64(0), C.c_int64(16), None, None, C.c_int64(16), C.c_int64(0),
-                                          ptr(tr.cum_table), ptr(tr.bucket_lo), C.byref(P), C.c_int32(1), ptr(tr.parts0[0]),
+        check(lib().n2v_sgns_train_groups(ptr(words), C.c_int64(0), C.c_int64(16), None, None, C.c_int64(16),
+                                          C.byref(P), C.c_int32(1), ptr(tr.parts0[0]),
                                           ptr(tr.parts1[0]), C.c_int32(0), C.c_int32(2), ptr(tr.pairs), stream()))
     P = tr._params(0, 4)
     P.window = 113                     # used to spin forever on sentences with > 256 kept tokens
