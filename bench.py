@@ -444,9 +444,11 @@ def run_ours(a):
                                                                               # bytes (ncu, same launch size) over the live kernel time
                 "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)", "peak_source": src,
-                "bound_note": "not HBM-bound: most rows are served by the 126 MB L2 (hit rate ~75 %); ncu shows issue slots "
-                              "~60 % busy and DRAM ~20 %: the kernel is bound by instruction issue and L2 row-transaction "
-                              "latency (DESIGN.md 3.4), so frac_model > frac_dram",
+                "bound_note": "not HBM-stream-bound: ~75 % of the rows are served by the 126 MB L2, so frac_model (row bytes the "
+                              "algorithm moves) exceeds frac_dram (bytes that reach HBM). What binds every SGNS kernel here is "
+                              "the rate at which L2 + HBM serve random 512-byte rows and row reductions: ~11 G row operations/s "
+                              "against 5.9 G reads/s or 4.7 G reductions/s from DRAM alone (DESIGN.md 3.4, "
+                              "profiles/r02_a_row_microbench.jsonl); halving the FMA issue slots (FFMA2) moved it by +2 %",
                 "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                 "algorithmic_bytes_per_pair": alg_bytes / my_pairs_rank, "pairs_per_launch": my_pairs_rank / n_launch,
                 ("carried_rows_per_launch" if block else "centres_per_launch"): centres / world / n_launch,

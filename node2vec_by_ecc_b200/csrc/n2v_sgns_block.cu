@@ -393,10 +393,14 @@ static int log2_parts(int32_t n_parts)
     return n_parts == 1 ? 0 : n_parts == 2 ? 1 : n_parts == 4 ? 2 : n_parts == 8 ? 3 : -1;
 }
 
+// per-(stream, sentence) word counts are int32, their running sum is not (8 parts x 4 M walks: > 2^31 words)
+struct WidenCount { __host__ __device__ int64_t operator()(int32_t c) const { return (int64_t)c; } };
+using WideCounts = cub::TransformInputIterator<int64_t, WidenCount, const int32_t *>;
+
 static size_t groups_scan_bytes(int64_t n)
 {
     size_t b = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int32_t *)nullptr, (int64_t *)nullptr, n);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, WideCounts((const int32_t *)nullptr, WidenCount()), (int64_t *)nullptr, n);
     return blk_align(b);
 }
 
@@ -452,7 +456,8 @@ extern "C" int n2v_sgns_groups_count(const int32_t *tokens, const int64_t *sent_
         sgns_groups_kernel<false><<<(unsigned)blocks, SGNS_BLOCK, 0, stream>>>(g);
         N2V_LAUNCH_CHECK();
     }
-    N2V_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const int32_t *)g.counts, offsets, n, stream));
+    N2V_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, WideCounts((const int32_t *)g.counts, WidenCount()), offsets, n,
+                                                 stream));
     return N2V_OK;
 }
 

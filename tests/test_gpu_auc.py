@@ -102,3 +102,46 @@ def test_block_auc_c2(c2, parts):
         s0, _ = tr.gather()
         runs.append(auc_of(c2, s0.cpu().numpy(), tr.order.cpu().numpy()))
     check(c2, runs, "block parts=%d" % parts)
+
+
+def test_c3_shaped_bipartite_auc_matches_oracle():
+    """C3 (BASELINE.json configs[2]) at 1/20 of its size: weighted user-item graph (lognormal user
+    activity, Zipf item popularity, weights 1..5; 10 k users + 40 k items, 1 M edges), whose edge tables do
+    not fit (the top item alone has ~9 % of the edges) -> weighted rejection walker with the folded return
+    edge, p=0.25 q=4. Same protocol as above, two seeds: device embeddings vs the CPU oracle's on the same
+    walks."""
+    from node2vec_by_ecc_b200 import DeviceGraph, WalkCorpus, Word2Vec, synth
+    nu, ni, m = 10_000, 40_000, 1_000_000
+    u, it, w, n = synth.bipartite_edges(nu, ni, m, seed=7, device="cuda")
+    edges = np.stack([u.cpu().numpy(), it.cpu().numpy()], 1).astype(np.int64)
+    wts = w.cpu().numpy()
+    idx = np.arange(len(edges))
+    tr_i, te_i = split_edges(idx)
+    tr, te = edges[tr_i], edges[te_i[:100_000]]
+    dg = DeviceGraph.from_coo(tr[:, 0], tr[:, 1], wts[tr_i], n, undirected=True)
+    assert dg.edge_table_bytes() > 8e9                     # the alias tables of this graph would not fit a budget
+    rng = np.random.RandomState(5)
+    true = set(map(tuple, edges.tolist()))
+    neg = []
+    while len(neg) < len(te):                              # user-item non-edges
+        a, b = int(rng.randint(0, nu)), int(nu + rng.randint(0, ni))
+        if (a, b) not in true:
+            neg.append((a, b))
+    neg = np.asarray(neg, dtype=np.int64)
+    starts = torch.arange(n, dtype=torch.int32).repeat(R)
+    dev_runs, ref_runs = [], []
+    for seed in (1, 2):
+        wk, ln = dg.walk_reject(0.25, 4.0, starts, L, seed=seed)
+        mdl = Word2Vec(WalkCorpus(wk, ln, None), size=128, window=10, min_count=0, sg=1, iter=1, seed=seed)
+        emb = np.zeros((n, 128), np.float32)
+        emb[np.asarray([int(x) for x in mdl.wv.index2word])] = mdl.wv.syn0
+        dev_runs.append(roc_auc_cosine(emb, te, neg))
+        wn = wk.cpu().numpy()
+        voc = oracle.sgns_vocab(wn, n)
+        tok = voc.id2index[np.maximum(wn, 0)].astype(np.int32); tok[wn < 0] = -1
+        off = np.arange(wn.shape[0] + 1, dtype=np.int64) * L
+        s0, _, _ = oracle.sgns_train(tok, off, voc, dim=128, window=10, negative=5, workers=os.cpu_count(), rng_mode=0, seed=seed)
+        emb = np.zeros((n, 128), np.float32); emb[voc.index2id] = s0
+        ref_runs.append(roc_auc_cosine(emb, te, neg))
+    assert np.isfinite(dev_runs).all() and min(ref_runs) > 0.5
+    assert abs(np.mean(dev_runs) - np.mean(ref_runs)) <= TOL, (dev_runs, ref_runs)
