@@ -212,6 +212,11 @@ typedef struct {
                                   1 = one set per centre, shared by its context pairs (dim<=128, k=5) */
     int32_t tuning;            /* 0 = default. bits 0-1: resident blocks/SM of the d<=128,k=5 kernel
                                   (1: 4, 2: 8, else 6); bit 3: force the generic kernel */
+    int32_t hot_rows;          /* negative_sharing kernels: negatives among the first hot_rows vocabulary rows (the
+                                  most frequent words) are NOT carried in registers across a centre's pairs but
+                                  re-read and reduced pair by pair. A carried copy is stale by what the other warps
+                                  holding the same row add meanwhile; for a hub word hundreds of warps hold it at
+                                  once. Sequential semantics are unchanged. 0 = carry every row. */
 } n2v_sgns_params_t;
 
 /* One pass over sentences [0, n_sent): tokens int32 ids (node ids if vocab_of_id != NULL,

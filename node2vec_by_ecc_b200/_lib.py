@@ -38,6 +38,7 @@ class SgnsParams(C.Structure):
         ("total_examples", C.c_int64), ("example_base", C.c_int64), ("sent_per_job", C.c_int64),
         ("epoch", C.c_uint32), ("seed", C.c_uint64),
         ("grid_warps", C.c_int32), ("atomic_updates", C.c_int32), ("negative_sharing", C.c_int32), ("tuning", C.c_int32),
+        ("hot_rows", C.c_int32),
     ]
 
 

@@ -412,6 +412,11 @@ sgns_train_kernel_v3(SgnsArgs a)
                         out[d + 1] = (on && tg[d] != centre) ? ldcg4(rows.r1(tg[d]), lane) : zero4;
 #pragma unroll
                     for (int d = 0; d < FN; ++d) if (tg[d] == centre) skipmask |= 2u << d;   // skipped, not redrawn
+                    // hot negatives (the most frequent words): not carried -- reduced and re-read pair by pair,
+                    // because hundreds of warps would hold stale copies of such a row at the same time
+                    uint32_t hotmask = 0u;
+#pragma unroll
+                    for (int d = 0; d < FN; ++d) if (tg[d] < a.p.hot_rows && !((skipmask >> (d + 1)) & 1u)) hotmask |= 2u << d;
 #pragma unroll
                     for (int d = 0; d <= FN; ++d) s_orig[wib][d][lane] = out[d];
                     int32_t j = (j0 == i) ? j0 + 1 : j0;
@@ -425,6 +430,10 @@ sgns_train_kernel_v3(SgnsArgs a)
                             if (on) prefetch_row_l2(rows.r1(tn), lane);
                         }
                     }
+                    // the centre's pairs. Two instantiations: centres whose set holds a hot row (rare on large
+                    // vocabularies) pay for the per-pair reductions / re-reads, the others run the lean loop
+                    auto pair_loop = [&](auto hot_tag) {
+                    constexpr bool HOT = decltype(hot_tag)::value;
                     while (j < kend) {
                         const int32_t ctx = ws.idx[j];
                         int32_t jn = j + 1; if (jn == i) ++jn;
@@ -466,7 +475,14 @@ sgns_train_kernel_v3(SgnsArgs a)
                         for (int d = 0; d <= FN; ++d) {       // g == 0: target skipped or |f| >= 6 (no-op)
                             const float g = __shfl_sync(0xFFFFFFFFu, gv, d * 4);
                             axpy4(work, g, out[d]);           // work += g * syn1neg[t]
-                            axpy4(out[d], g, row1);           // syn1neg[t] += g * row1 (carried)
+                            if (HOT && d > 0 && ((hotmask >> d) & 1u)) {   // hot row: update now, take the row as it is now
+                                float *const rp = rows.r1(tg[d - 1]);
+                                axpy4(out[d], g, row1);
+                                add_row<ATOMIC>(rp, lane, make_float4(g * row1.x, g * row1.y, g * row1.z, g * row1.w), out[d], on);
+                                if (ATOMIC) out[d] = on ? ldcg4(rp, lane) : zero4;
+                            } else {
+                                axpy4(out[d], g, row1);       // syn1neg[t] += g * row1 (carried)
+                            }
                         }
                         float4 upd1 = row1;
                         upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
@@ -475,11 +491,13 @@ sgns_train_kernel_v3(SgnsArgs a)
                         row1 = row1n;
                         if (stale && j < kend) row1 = on ? ldcg4(rows.r0(ctx), lane) : zero4;   // re-read after the update
                     }
+                    };
+                    if (hotmask) pair_loop(std::true_type{}); else pair_loop(std::false_type{});
                     pairs += (unsigned long long)(kend - j0 - ((i >= j0 && i < kend) ? 1 : 0));
                     // one reduction per carried row: what this centre's pairs added to it
 #pragma unroll
                     for (int d = 0; d <= FN; ++d) {
-                        if ((skipmask >> d) & 1u) continue;
+                        if (((skipmask | hotmask) >> d) & 1u) continue;
                         const float4 og = s_orig[wib][d][lane];
                         const float4 dl = make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w);
                         add_row<ATOMIC>(rows.r1(d == 0 ? centre : tg[d - 1]), lane, dl, out[d], on);

@@ -36,6 +36,7 @@
 // Work distribution: warp w owns one contiguous range of the stream (whole groups), i.e. consecutive
 // walks, so concurrent warps work on far-apart walks as the sentence-major kernels do.
 #include <cub/cub.cuh>
+#include <type_traits>
 
 #include "n2v_common.cuh"
 #include "n2v_sgns_stage.cuh"
@@ -235,10 +236,12 @@ sgns_group_kernel(TrainGroupsArgs a)
 #pragma unroll
     for (int d = 0; d < FN; ++d) tg[d] = 0;
     uint32_t alpha_s = 0xFFFFFFFFu; float alpha = 0.f;
+    uint32_t set_hot = 0u;                                     // negatives of the live set that are not carried (hot rows)
     auto flush_set = [&]() {
         if (set_live && !set_dup) {
 #pragma unroll
             for (int d = 1; d <= FN; ++d) {
+                if ((set_hot >> d) & 1u) continue;
                 const float4 og = s_orig[wib][d][lane];
                 add_row<ATOMIC>(rows.r1(tg[d - 1]), lane,
                                 make_float4(out[d].x - og.x, out[d].y - og.y, out[d].z - og.z, out[d].w - og.w), out[d], on);
@@ -281,7 +284,12 @@ sgns_group_kernel(TrainGroupsArgs a)
             for (int d1 = 0; d1 < FN; ++d1)
 #pragma unroll
                 for (int d2 = d1 + 1; d2 < FN; ++d2) set_dup |= (tg[d1] == tg[d2]);
+            set_hot = 0u;
             if (!set_dup) {
+                // hot negatives (vocabulary row = local row * n_parts + part below hot_rows): reduced and re-read pair
+                // by pair instead of carried (n2v_sgns.cu v3 says why)
+#pragma unroll
+                for (int d = 0; d < FN; ++d) if ((((int64_t)tg[d] << a.lg) | a.part) < a.p.hot_rows) set_hot |= 2u << d;
 #pragma unroll
                 for (int d = 0; d < FN; ++d) out[d + 1] = on ? ldcg4(rows.r1(tg[d]), lane) : zero4;
 #pragma unroll
@@ -312,6 +320,9 @@ sgns_group_kernel(TrainGroupsArgs a)
                     }
                 }
             }
+            // two instantiations of the pair loop: sets with a hot row pay for the per-pair reductions / re-reads
+            auto pair_loop = [&](auto hot_tag) {
+            constexpr bool HOT = decltype(hot_tag)::value;
             while (j < cnt) {
                 const int32_t jn = j + 1;
                 // next input row always in flight (clamped past the group's end); it is stale only if it
@@ -348,6 +359,11 @@ sgns_group_kernel(TrainGroupsArgs a)
                     const float gd = __shfl_sync(0xFFFFFFFFu, gv, d * 4);
                     axpy4(work, gd, out[d]);
                     axpy4(out[d], gd, row1);
+                    if (HOT && d > 0 && ((set_hot >> d) & 1u) && !((skipmask >> d) & 1u)) {   // hot row: update now, re-read
+                        float *const rp = rows.r1(tg[d - 1]);
+                        add_row<ATOMIC>(rp, lane, make_float4(gd * row1.x, gd * row1.y, gd * row1.z, gd * row1.w), out[d], on);
+                        if (ATOMIC) out[d] = on ? ldcg4(rp, lane) : zero4;
+                    }
                 }
                 float4 upd1 = row1;
                 upd1.x += work.x; upd1.y += work.y; upd1.z += work.z; upd1.w += work.w;
@@ -357,6 +373,8 @@ sgns_group_kernel(TrainGroupsArgs a)
                 if (stale && j < cnt) row1 = on ? ldcg4(rows.r0(ctx), lane) : zero4;   // re-read after the update
                 ctx = ctx_n;
             }
+            };
+            if (set_hot) pair_loop(std::true_type{}); else pair_loop(std::false_type{});
             {                                          // the centre row: one reduction of what this group added
                 const float4 og = s_orig[wib][0][lane];
                 add_row<ATOMIC>(rows.r1(centre), lane,

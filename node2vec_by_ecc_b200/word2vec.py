@@ -202,6 +202,7 @@ class SgnsTrainer:
                                  ptr(self.cum_table), ptr(self.bucket_lo), C.c_int32(self.bucket_bits),
                                  ptr(ws), C.c_size_t(ws_bytes), stream()))
         self.pairs = torch.zeros(2, dtype=torch.int64, device=dev)   # [pairs, carried centres]
+        self._neg_prob = None
         self.reset_weights()
 
     def reset_weights(self):
@@ -210,6 +211,24 @@ class SgnsTrainer:
         self.syn1neg = torch.empty((self.V, self.dim), dtype=torch.float32, device=dev)
         check(lib().n2v_sgns_init(ptr(self.syn0), ptr(self.syn1neg), C.c_int32(self.V), C.c_int32(self.dim),
                                   C.c_uint64(self.seed), stream()))
+
+    def hot_rows(self, grid_warps: int) -> int:
+        """Vocabulary rows (a prefix: the table is count-sorted) whose negatives the shared-negative kernels
+        must not carry in registers. A negative row is held by about c = grid_warps * 5 * p warps at once
+        (p = its share of the count^0.75 mass), each copy stale by what the others add meanwhile; rows with
+        c above N2V_SGNS_HOT_COPIES (default 1) are re-read and reduced pair by pair instead. Measured on
+        a Zipf(1.0) user-item graph (tests/test_gpu_auc.py, scripts/hot_rows_sweep.py): carrying everything
+        at full width moved the link-prediction AUC by +0.019 against the same law run narrow or on the
+        CPU; +0.009 with only the hubs (c > 8) uncarried, +0.0006 with c > 0.3. N2V_SGNS_HOT_ROWS overrides
+        the count directly."""
+        env = os.environ.get("N2V_SGNS_HOT_ROWS")
+        if env is not None:
+            return int(env)
+        if self._neg_prob is None:
+            cum = self.cum_table.to(torch.int64)
+            self._neg_prob = (torch.diff(cum, prepend=cum.new_zeros(1)).to(torch.float64) / float(cum[-1].item())).cpu()
+        tau = float(os.environ.get("N2V_SGNS_HOT_COPIES", "1")) / (5.0 * max(int(grid_warps), 1))
+        return int((self._neg_prob > tau).sum().item())
 
     def default_hogwild_warps(self, shared: bool = False) -> int:
         """Concurrent sentences. gensim runs `workers` (8-12) sentences at a time against the shared
@@ -221,7 +240,7 @@ class SgnsTrainer:
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
               epoch=0, sent_per_job=125, grid_warps=None, atomic_updates=1, alpha=None, min_alpha=None,
-              tuning=None, negative_sharing=0, vocab_of_id=None):
+              tuning=None, negative_sharing=0, vocab_of_id=None, hot_rows=None):
         """One pass over n_sent sentences (asynchronous on the current stream); self.pairs
         (device int64) accumulates the (centre, context) pairs trained. vocab_of_id: token id ->
         vocabulary row (-1 = not in the vocabulary) when the tokens are not in the id space the
@@ -238,6 +257,7 @@ class SgnsTrainer:
         P.atomic_updates = int(atomic_updates)
         P.negative_sharing = int(negative_sharing)
         P.tuning = int(os.environ.get("N2V_SGNS_TUNING", "0")) if tuning is None else int(tuning)
+        P.hot_rows = (self.hot_rows(P.grid_warps) if hot_rows is None else int(hot_rows)) if negative_sharing else 0
         check(lib().n2v_sgns_train(ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride),
                                    C.c_int64(sent_id_base), ptr(self.vocab_of_id if vocab_of_id is None else vocab_of_id),
                                    ptr(self.keep_thr if self.sample > 0 else None), ptr(self.cum_table),
@@ -304,6 +324,7 @@ class PeerSgnsTrainer(SgnsTrainer):
         P.epoch, P.seed = int(epoch), self.seed
         P.grid_warps = int(grid_warps or self.default_hogwild_warps(True))
         P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
+        P.hot_rows = self.hot_rows(P.grid_warps)
         check(lib().n2v_sgns_train_sharded(ptr(tokens), ptr(sent_off), C.c_int64(n_sent), C.c_int32(stride),
                                            C.c_int64(sent_id_base), ptr(self.vocab_of_id),
                                            ptr(self.keep_thr if self.sample > 0 else None), ptr(self.cum_table),
@@ -395,7 +416,7 @@ class BlockSgnsTrainer(SgnsTrainer):
         return int(max(4, min(sms * 20, (self.V // self.n_parts) // 4)))
 
     def _params(self, epoch, grid_warps, *, total_examples=1, example_base=0, sent_per_job=1, alpha=None,
-                min_alpha=None):
+                min_alpha=None, hot_rows=None):
         P = SgnsParams()
         P.V, P.dim, P.window, P.negative = self.V, self.dim, self.window, self.negative
         P.bucket_bits, P.max_sentence_len = self.bucket_bits, 10000
@@ -406,6 +427,7 @@ class BlockSgnsTrainer(SgnsTrainer):
         P.epoch, P.seed = int(epoch), self.seed
         P.grid_warps = int(grid_warps or self.default_hogwild_warps())
         P.atomic_updates, P.negative_sharing, P.tuning = 1, 1, 0
+        P.hot_rows = self.hot_rows(P.grid_warps) if hot_rows is None else int(hot_rows)
         return P
 
     def make_groups(self, tokens, sent_off, n_sent, stride, sent_id_base, P, part, exact_bounds=True):
@@ -459,7 +481,8 @@ class BlockSgnsTrainer(SgnsTrainer):
                                           C.c_int32(part), C.c_int32(self.n_parts), ptr(self.pairs), stream()))
 
     def train(self, tokens, sent_off, n_sent, stride, *, total_examples, example_base=0, sent_id_base=0,
-              epoch=0, sent_per_job=125, grid_warps=None, alpha=None, min_alpha=None, exact_bounds=True, **_ignored):
+              epoch=0, sent_per_job=125, grid_warps=None, alpha=None, min_alpha=None, exact_bounds=True, hot_rows=None,
+              **_ignored):
         """One pool. Multi-GPU: every rank passes its own walks (fixed-stride buffer, same n_sent on
         every rank) and the POOL's example_base / sent_id_base (identical on all ranks)."""
         from . import dist as D
@@ -476,7 +499,7 @@ class BlockSgnsTrainer(SgnsTrainer):
             return
         t = mark("gather", t)
         P = self._params(epoch, grid_warps, total_examples=total_examples, example_base=example_base,
-                         sent_per_job=sent_per_job, alpha=alpha, min_alpha=min_alpha)
+                         sent_per_job=sent_per_job, alpha=alpha, min_alpha=min_alpha, hot_rows=hot_rows)
         streams = {k: self.make_groups(tokens, sent_off, n_sent, stride, sent_id_base, P, k, exact_bounds)
                    for k in self._mine}
         t = mark("pairs", t)

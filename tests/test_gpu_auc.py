@@ -106,10 +106,10 @@ def test_block_auc_c2(c2, parts):
 
 def test_c3_shaped_bipartite_auc_matches_oracle():
     """C3 (BASELINE.json configs[2]) at 1/20 of its size: weighted user-item graph (lognormal user
-    activity, Zipf item popularity, weights 1..5; 10 k users + 40 k items, 1 M edges), whose edge tables do
-    not fit (the top item alone has ~9 % of the edges) -> weighted rejection walker with the folded return
-    edge, p=0.25 q=4. Same protocol as above, two seeds: device embeddings vs the CPU oracle's on the same
-    walks."""
+    activity, Zipf item popularity, weights 1..5; 10 k users + 40 k items, 1 M edges) -> weighted rejection walker with the folded return
+    edge (what a graph of C3's size has to use), p=0.25 q=4. Same protocol as above, two seeds: each device law vs
+    the same law of the CPU oracle on the same walks. This is the graph on which carrying hub negatives in
+    registers at full Hogwild width moved the AUC by +0.019 (SgnsTrainer.hot_rows)."""
     from node2vec_by_ecc_b200 import DeviceGraph, WalkCorpus, Word2Vec, synth
     nu, ni, m = 10_000, 40_000, 1_000_000
     u, it, w, n = synth.bipartite_edges(nu, ni, m, seed=7, device="cuda")
@@ -119,7 +119,7 @@ def test_c3_shaped_bipartite_auc_matches_oracle():
     tr_i, te_i = split_edges(idx)
     tr, te = edges[tr_i], edges[te_i[:100_000]]
     dg = DeviceGraph.from_coo(tr[:, 0], tr[:, 1], wts[tr_i], n, undirected=True)
-    assert dg.edge_table_bytes() > 8e9                     # the alias tables of this graph would not fit a budget
+    assert dg.edge_table_bytes() > 2e9          # 2.8 GB of edge tables for 50 k nodes (2.6 TB at the full C3 size)
     rng = np.random.RandomState(5)
     true = set(map(tuple, edges.tolist()))
     neg = []
@@ -129,19 +129,29 @@ def test_c3_shaped_bipartite_auc_matches_oracle():
             neg.append((a, b))
     neg = np.asarray(neg, dtype=np.int64)
     starts = torch.arange(n, dtype=torch.int32).repeat(R)
-    dev_runs, ref_runs = [], []
+    runs = {"dev shared": [], "dev per-pair": [], "ref shared": [], "ref per-pair": []}
     for seed in (1, 2):
         wk, ln = dg.walk_reject(0.25, 4.0, starts, L, seed=seed)
-        mdl = Word2Vec(WalkCorpus(wk, ln, None), size=128, window=10, min_count=0, sg=1, iter=1, seed=seed)
-        emb = np.zeros((n, 128), np.float32)
-        emb[np.asarray([int(x) for x in mdl.wv.index2word])] = mdl.wv.syn0
-        dev_runs.append(roc_auc_cosine(emb, te, neg))
+        for key, shared in (("dev shared", 1), ("dev per-pair", 0)):
+            mdl = Word2Vec(WalkCorpus(wk, ln, None), size=128, window=10, min_count=0, sg=1, iter=1, seed=seed,
+                           shared_negatives=shared)
+            emb = np.zeros((n, 128), np.float32)
+            emb[np.asarray([int(x) for x in mdl.wv.index2word])] = mdl.wv.syn0
+            runs[key].append(roc_auc_cosine(emb, te, neg))
+            if shared:
+                assert mdl.trainer.hot_rows(mdl.trainer.default_hogwild_warps(True)) > 20     # the rule is in play here
         wn = wk.cpu().numpy()
         voc = oracle.sgns_vocab(wn, n)
         tok = voc.id2index[np.maximum(wn, 0)].astype(np.int32); tok[wn < 0] = -1
         off = np.arange(wn.shape[0] + 1, dtype=np.int64) * L
-        s0, _, _ = oracle.sgns_train(tok, off, voc, dim=128, window=10, negative=5, workers=os.cpu_count(), rng_mode=0, seed=seed)
-        emb = np.zeros((n, 128), np.float32); emb[voc.index2id] = s0
-        ref_runs.append(roc_auc_cosine(emb, te, neg))
-    assert np.isfinite(dev_runs).all() and min(ref_runs) > 0.5
-    assert abs(np.mean(dev_runs) - np.mean(ref_runs)) <= TOL, (dev_runs, ref_runs)
+        for key, mode in (("ref per-pair", 0), ("ref shared", 2)):
+            s0, _, _ = oracle.sgns_train(tok, off, voc, dim=128, window=10, negative=5, workers=os.cpu_count(), rng_mode=mode, seed=seed)
+            emb = np.zeros((n, 128), np.float32); emb[voc.index2id] = s0
+            runs[key].append(roc_auc_cosine(emb, te, neg))
+    mean = {k: float(np.mean(v)) for k, v in runs.items()}
+    # like for like: each device law against the same law on the CPU
+    assert abs(mean["dev per-pair"] - mean["ref per-pair"]) <= TOL, runs
+    assert abs(mean["dev shared"] - mean["ref shared"]) <= TOL, runs
+    # the two LAWS differ more here than on C2 (a user-item edge is scored by the cosine of two rows that are
+    # never each other's context: AUC < 0.5, and sharing a centre's negatives shifts it by ~0.006 on the CPU too)
+    assert abs(mean["ref shared"] - mean["ref per-pair"]) <= 0.01, runs

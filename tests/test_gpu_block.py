@@ -101,9 +101,10 @@ def test_group_streams_ragged_long_sentences():
             assert np.array_equal(got[bounds[b]:bounds[b + 1]], want[b])
 
 
-@pytest.mark.parametrize("n_parts,dim,neg_group,warps", [(1, 128, 1, 1), (2, 128, 1, 1), (4, 64, 1, 1), (8, 128, 1, 1),
-                                                        (4, 128, 3, 1), (2, 128, 1, 3)])
-def test_block_schedule_sequential_equals_oracle(n_parts, dim, neg_group, warps):
+@pytest.mark.parametrize("n_parts,dim,neg_group,warps,hot", [(1, 128, 1, 1, 0), (2, 128, 1, 1, 0), (4, 64, 1, 1, 0), (8, 128, 1, 1, 0),
+                                                            (4, 128, 3, 1, 0), (2, 128, 1, 3, 0), (2, 128, 1, 1, 1 << 30),
+                                                            (4, 128, 3, 1, 6)])
+def test_block_schedule_sequential_equals_oracle(n_parts, dim, neg_group, warps, hot):
     """one warp per launch == the oracle's restatement of the schedule, two pools (alpha moves on);
     with 3 warps the three contiguous thirds of every stream run concurrently -- on karate they share
     all 34 rows, so that case only checks the pair count"""
@@ -122,7 +123,7 @@ def test_block_schedule_sequential_equals_oracle(n_parts, dim, neg_group, warps)
     pairs = 0
     for a, b in [(0, half), (half, n_tot)]:
         tr.train(walks[a:b], None, b - a, L, total_examples=n_tot, example_base=a, sent_id_base=a, sent_per_job=25,
-                 grid_warps=warps)
+                 grid_warps=warps, hot_rows=hot)
         pairs += oracle.sgns_block_pool(tok[a * L: b * L], off[: b - a + 1], voc, parts0, parts1, window=10,
                                         alpha=0.025, total_examples=n_tot, example_base=a, sent_per_job=25,
                                         neg_group=neg_group, seed=4, epoch=0, sent_id_base=a)

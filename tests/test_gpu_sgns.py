@@ -117,6 +117,27 @@ def test_shared_negative_mode_sequential_equals_oracle(size, iters, sample, case
     assert np.abs(s0p - s0).max() > 1e-3
 
 
+@pytest.mark.parametrize("atomic,hot", [(1, 1 << 30), (0, 1 << 30), (1, 5)])
+def test_hot_rows_keep_the_sequential_semantics(monkeypatch, atomic, hot):
+    """negatives among the `hot_rows` most frequent words are reduced and re-read pair by pair instead
+    of carried across the centre's window (bounded staleness under wide Hogwild): with one warp the run
+    still equals the oracle's shared-negative law -- every row hot, the top 5 hot, both update modes"""
+    from node2vec_by_ecc_b200 import Word2Vec
+    monkeypatch.setenv("N2V_SGNS_HOT_ROWS", str(hot))
+    z, g, corpus = corpus_from_golden("rndw_p05_q2")
+    m = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, negative=5, seed=3, hogwild_warps=1,
+                 shared_negatives=1, atomic_updates=atomic)
+    tok, off, voc = oracle_inputs(m, z["walks"])
+    s0, s1, pairs = oracle.sgns_train(tok, off, voc, dim=128, window=10, negative=5, iters=1, workers=1, rng_mode=3, seed=3)
+    assert m.pairs_trained == pairs
+    assert np.abs(m.wv.syn0 - s0).max() < 2e-4 and np.abs(m.syn1neg_dev.cpu().numpy() - s1).max() < 2e-4
+    # the rule itself: rows whose count^0.75 share puts more than ~8 copies in flight at the given width
+    monkeypatch.delenv("N2V_SGNS_HOT_ROWS")
+    T = m.trainer
+    assert T.hot_rows(1) == 0 and 0 < T.hot_rows(100000) <= T.V
+    assert T.hot_rows(100000) >= T.hot_rows(1000)
+
+
 def test_atomic_update_mode_sequential_equals_plain():
     from node2vec_by_ecc_b200 import Word2Vec
     _, _, corpus = corpus_from_golden()
