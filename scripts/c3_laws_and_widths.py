@@ -1,3 +1,4 @@
+"""C3-shaped user-item graph (tests/test_gpu_auc.py): link-prediction AUC of both device laws at full and narrow Hogwild\nwidth against the CPU oracle under both laws (16 workers and 1 worker) on the same walks."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
