@@ -105,6 +105,9 @@ def parse():
     ap.add_argument("--neg-group", type=int, default=1,
                     help="block mode: token positions of a walk whose centres share one negative set (1 = one set per "
                          "centre occurrence, the single-GPU law)")
+    ap.add_argument("--sgns-variant", default="default", choices=["default", "mma"],
+                    help="mma = the tensor-core window-batch experiment (csrc/n2v_sgns_mma.cu; one GPU, shared negatives): "
+                         "timed for DESIGN.md 3.4's choice, not a parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-walks", type=int, default=0, help="walks per reference-arm step (0 = auto)")
@@ -423,6 +426,8 @@ def run_ours(a):
             alg_bytes = (my_pairs_rank * 1024.0 + centres / world * 6144.0)
             kshort = "sgns_train_kernel_v3"
             kname = "sgns_train_kernel_v3 (one negative set per centre occurrence)"
+            if a.sgns_variant == "mma":
+                kshort = kname = "sgns_train_kernel_mma (EXPERIMENT: window-batch semantics, TF32 tensor cores)"
         else:
             alg_bytes = my_pairs_rank * float(BYTES_PER_PAIR)
             kshort = "sgns_train_kernel_v2"
@@ -640,6 +645,8 @@ def run_reference(a):
 
 if __name__ == "__main__":
     args = parse()
+    if args.sgns_variant == "mma":
+        os.environ["N2V_SGNS_TUNING"] = "16"
     # stdout carries exactly one JSON line: anything libraries print (NCCL banners ...) goes to stderr
     _real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)

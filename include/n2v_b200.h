@@ -211,7 +211,8 @@ typedef struct {
     int32_t negative_sharing;  /* 0 = fresh negatives for every (centre, context) pair (gensim);
                                   1 = one set per centre, shared by its context pairs (dim<=128, k=5) */
     int32_t tuning;            /* 0 = default. bits 0-1: resident blocks/SM of the d<=128,k=5 kernel
-                                  (1: 4, 2: 8, else 6); bit 3: force the generic kernel */
+                                  (1: 4, 2: 8, else 6); bit 3: force the generic kernel; bit 4 (with
+                                  negative_sharing): the tensor-core window-batch experiment (n2v_sgns_mma.cu) */
     int32_t hot_rows;          /* negative_sharing kernels: negatives among the first hot_rows vocabulary rows (the
                                   most frequent words) are NOT carried in registers across a centre's pairs but
                                   re-read and reduced pair by pair. A carried copy is stale by what the other warps

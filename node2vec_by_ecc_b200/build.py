@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libn2v_b200.so")
-SOURCES = ["n2v_core.cu", "n2v_alias.cu", "n2v_walk.cu", "n2v_walk2.cu", "n2v_walk3.cu", "n2v_sgns.cu", "n2v_sgns_block.cu", "n2v_score.cu", "n2v_format.cu", "n2v_bench.cu"]
+SOURCES = ["n2v_core.cu", "n2v_alias.cu", "n2v_walk.cu", "n2v_walk2.cu", "n2v_walk3.cu", "n2v_sgns.cu", "n2v_sgns_mma.cu", "n2v_sgns_block.cu", "n2v_score.cu", "n2v_format.cu", "n2v_bench.cu"]
 
 
 def nvcc_path() -> str:

@@ -522,6 +522,8 @@ sgns_train_kernel_v3(SgnsArgs a)
     if (lane == 0 && a.pairs_out && pairs) { atomicAdd(a.pairs_out, pairs); atomicAdd(a.pairs_out + 1, centres); }
 }
 
+int launch_train_mma(const SgnsArgs &a, cudaStream_t stream);     // n2v_sgns_mma.cu
+
 template <int NV>
 static int launch_train(const SgnsArgs &a, cudaStream_t stream)
 {
@@ -669,6 +671,7 @@ static int sgns_train_impl(const int32_t *tokens, const int64_t *sent_off, int64
         while ((1 << a.parts_log2) < n_parts) ++a.parts_log2;
     }
     const int nv = (p.dim + 127) / 128;
+    if (p.negative_sharing && (p.tuning & 16) && a.parts_log2 < 0) return launch_train_mma(a, stream);   // experiment (n2v_sgns_mma.cu)
     if (p.negative_sharing) {
         N2V_REQUIRE(nv == 1 && p.negative == 5, "negative_sharing needs dim <= 128 and negative == 5");
         const int blocks = (p.grid_warps + SGNS_BLOCK / 32 - 1) / (SGNS_BLOCK / 32);

@@ -138,6 +138,21 @@ def test_hot_rows_keep_the_sequential_semantics(monkeypatch, atomic, hot):
     assert T.hot_rows(100000) >= T.hot_rows(1000)
 
 
+def test_tensor_core_window_batch_experiment_trains(monkeypatch):
+    """csrc/n2v_sgns_mma.cu (N2V_SGNS_TUNING=16): the same pairs and negative sets as the shared-negative
+    kernel, window-batch semantics on TF32 tensor cores -- not a parity mode; here only: same pair count,
+    finite tables, rows close to the sequential kernel's"""
+    from node2vec_by_ecc_b200 import Word2Vec
+    _, _, corpus = corpus_from_golden("rndw_p05_q2")
+    ref = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, seed=3, hogwild_warps=1, shared_negatives=1)
+    monkeypatch.setenv("N2V_SGNS_TUNING", "16")
+    m = Word2Vec(corpus, size=128, window=10, min_count=0, sg=1, iter=1, seed=3, hogwild_warps=1, shared_negatives=1)
+    assert m.pairs_trained == ref.pairs_trained and np.isfinite(m.wv.syn0).all()
+    a, b = m.wv.syn0, ref.wv.syn0
+    cos = (a * b).sum(1) / np.linalg.norm(a, axis=1) / np.linalg.norm(b, axis=1)
+    assert np.abs(a - oracle.sgns_init_syn0(a.shape[0], 128, 3)).max() > 0.01 and cos.mean() > 0.9, cos.mean()
+
+
 def test_atomic_update_mode_sequential_equals_plain():
     from node2vec_by_ecc_b200 import Word2Vec
     _, _, corpus = corpus_from_golden()
