@@ -41,6 +41,17 @@ def step_walk_ids(step: int, rank: int, world_size: int, batch: int):
     return (step * world_size + rank) * batch
 
 
+def pool_plan(total: int, world_size: int, pool_walks: int):
+    """How a corpus of `total` walks, cut into `world_size` contiguous shares (shard_range), is trained by
+    the block-partitioned trainer: -> (per, pools) with per = walks per rank after padding every share to
+    one length (empty walks add no pairs) and pools = [(first walk of the share, walks per rank)], the same
+    on every rank -- all ranks must run the same number of pools of the same size, because every pool ends
+    in collectives. Pool p covers the global example range [first * world, (first + n) * world)."""
+    per = int(math.ceil(float(total) / world_size)) if total else 0
+    pool = int(max(1, min(per, pool_walks))) if per else 1
+    return per, [(p0, min(pool, per - p0)) for p0 in range(0, per, pool)]
+
+
 def sum_counts(counts: torch.Tensor) -> torch.Tensor:
     if world()[1] > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)

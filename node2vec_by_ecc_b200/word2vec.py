@@ -747,17 +747,16 @@ class Word2Vec:
     def _train_sharded(self, tok, n_sent, stride, epochs, start_alpha, end_alpha):
         """every rank's share of the corpus, pool by pool (pool = the same slice of every rank's share;
         shares are padded with empty walks to one length so that all ranks run the same pools)"""
+        from . import dist as D
         T = self.trainer
         rank, world, total = self._shard
-        per = -(-total // world)
+        per, pools = D.pool_plan(total, world, max(1024, int(os.environ.get("N2V_POOL_WALKS", str(1 << 19)))))
         if n_sent < per:
             tok = torch.cat([tok, torch.full((per - n_sent, stride), -1, dtype=tok.dtype, device=tok.device)])
-        pool = int(min(per, max(1024, int(os.environ.get("N2V_POOL_WALKS", str(1 << 19))))))
         mean_len = max(1.0, T.raw_words / max(self.corpus_count, 1))
         before = T.pairs[0].clone()
         for ep in range(epochs):
-            for p0 in range(0, per, pool):
-                n = min(pool, per - p0)
+            for p0, n in pools:
                 T.train(tok[p0:p0 + n].contiguous(), None, n, stride, total_examples=max(1, per * world * epochs),
                         example_base=(ep * per + p0) * world, sent_id_base=(ep * per + p0) * world, epoch=ep,
                         sent_per_job=int(self.batch_words // mean_len), grid_warps=self.hogwild_warps,

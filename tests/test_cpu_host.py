@@ -202,6 +202,51 @@ def _gloo_block_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_plan_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from node2vec_by_ecc_b200.dist import pool_plan, shard_range, sum_counts
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    total = 1003                                   # walks of the whole corpus; shares: 502 + 501
+    lo, hi = shard_range(total, rank, world)
+    per, pools = pool_plan(total, world, 200)
+    # what Graph(distributed=True).simulate_walks + Word2Vec._train_sharded do with their share
+    mine = torch.arange(lo, hi)                    # global walk ids of this rank's share
+    padded = torch.cat([mine, torch.full((per - mine.numel(),), -1)])
+    seen = []
+    for p0, n in pools:
+        part = padded[p0:p0 + n]
+        got = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(got, part)                 # the pool: rank 0's slice, then rank 1's (gather_pool order)
+        seen.append(torch.cat(got))
+    counts = sum_counts(torch.bincount(mine % 7, minlength=7))
+    q.put((rank, per, pools, torch.cat(seen).tolist(), counts.tolist()))
+    dist.destroy_process_group()
+
+
+def test_gloo_sharded_corpus_pool_plan():
+    """the host arithmetic behind Graph(distributed=True) + Word2Vec on a sharded corpus: contiguous shares
+    (main_link.py:263-264), padded to one length, the same pools on every rank, every walk in exactly one
+    pool, vocabulary counts summed"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gloo_plan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, per0, pools0, seen0, c0), (_, per1, pools1, seen1, c1) = res
+    assert per0 == per1 == 502 and pools0 == pools1 == [(0, 200), (200, 200), (400, 102)]
+    assert seen0 == seen1                                             # every rank assembles the same pools
+    real = [x for x in seen0 if x >= 0]
+    assert sorted(real) == list(range(1003)) and len(seen0) == 2 * 502    # one empty walk pads the short share
+    assert c0 == c1 == torch.bincount(torch.arange(1003) % 7, minlength=7).tolist()
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_gloo_block_schedule_ring(world):
     """BlockSgnsTrainer's host plumbing: pool gathered in rank order; in every sub-step the ranks
