@@ -322,6 +322,8 @@ def run_ours(a):
         trainer.phase_events = []
     ms, pairs, cn, centres = timed(a.warmup, record=True)
     clocks = sampler.stop()
+    if block:
+        trainer.check_overflow()          # device-side stream bounds: a pool that did not fit its buffer would show here
     phases = None
     if block:     # rank 0's split of the SGNS phase: pool all-gather, pair expansion, bucket kernels, ring passes
         phases = {}
