@@ -160,12 +160,10 @@ def per_row_top_k(emb, rows, k, *, centered=False, sample_cols=1024):
         src, dst, s = src[keep], dst[keep], s[keep]
         cnt = torch.bincount(src, minlength=n)
         short = (cnt[todo] < k)
-        ok_rows = todo[~short]
         sel = ~short[torch.searchsorted(todo, src)]
         done_src.append(src[sel]); done_dst.append(dst[sel]); done_s.append(s[sel])
         todo = todo[short]
         thr_row[todo] = NEG_INF                                 # too few survivors in these rows: take everything
-        del ok_rows
     src, dst, s = torch.cat(done_src), torch.cat(done_dst), torch.cat(done_s)
     # per row: score descending, ties by column (the reference's stable sort over user order, :391)
     o = torch.argsort(dst, stable=True)
