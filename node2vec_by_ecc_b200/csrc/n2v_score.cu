@@ -88,11 +88,11 @@ sim_threshold_kernel(SimArgs g)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int32_t r0 = blockIdx.y * ST_TILE, c0 = blockIdx.x * ST_TILE;
     if (g.upper_only && c0 + ST_TILE - 1 <= r0) return;            // tile entirely on or below the diagonal
-    float acc[4][4];
+    // accumulators as packed fp32 pairs (FFMA2: one issue slot for two fused multiply-adds): acc2[i][h] holds
+    // outputs (row i, columns 2h and 2h + 1)
+    unsigned long long acc2[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i) acc2[i][0] = acc2[i][1] = 0ull;
     // the tile's excluded pairs: one row per thread, a bit per column
     if (tid < ST_TILE) {
         unsigned long long m = 0ull;
@@ -134,15 +134,27 @@ sim_threshold_kernel(SimArgs g)
         for (int kk = 0; kk < ST_K; ++kk) {
             const float4 a4 = *reinterpret_cast<const float4 *>(&sA[kk][ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4 *>(&sB[kk][tx * 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            unsigned long long b01, b23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b01) : "f"(b4.x), "f"(b4.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b23) : "f"(b4.z), "f"(b4.w));
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+            for (int i = 0; i < 4; ++i) {
+                unsigned long long aa;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(av[i]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][0]) : "l"(aa), "l"(b01));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][1]) : "l"(aa), "l"(b23));
+            }
         }
         __syncthreads();
     }
     // epilogue: normalise, mask, select, emit
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][0]), "=f"(acc[i][1]) : "l"(acc2[i][0]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2]), "=f"(acc[i][3]) : "l"(acc2[i][1]));
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int32_t r = r0 + ty * 4 + i;
