@@ -13,11 +13,17 @@ path over one batch: `batch_walks` walks per GPU are simulated (n2v_walk_reject)
 trained on (n2v_sgns_train); with N > 1 the walk ids of a step are split across ranks (weak
 scaling: batch per GPU fixed) and SGNS runs block-partitioned (--multi-gpu-sgns block, the
 default): the tables are cut into N row sets, the step's walks of all GPUs form one pool, GPU k
-trains the pair bucket (centre in part k, context in part (k + e) % N) in sub-step e and the syn0
+trains the group stream (centre in part k, context in part (k + e) % N) in sub-step e and the syn0
 parts travel round an NCCL ring -- no replicas (node2vec_by_ecc_b200.word2vec.BlockSgnsTrainer).
 `replica` (full copies, delta-sum all-reduce every `sync_walks` walks) and `peer` (one table pair
 in NVLink peer memory) are the measured alternatives.
 value = (centre, context) pairs trained per second through the whole step, all ranks.
+e2e = the same step through the reference-facing classes with host buffers: start nodes in pinned host memory
+-> node2vec.Graph.simulate_walks -> walks copied back to pinned host memory -> gensim-style Word2Vec.train on
+the returned corpus -> pair count read back (at N > 1: Graph(distributed=True), block-partitioned Word2Vec).
+roofline: frac_model / frac_8d / frac_dram = the kernel time against its own algorithmic row bytes, SURVEY 8d's
+7,168 B/pair, and the DRAM bytes ncu measured (profiles/ncu_traffic.json, refused when the kernel sources
+changed since the capture). Block mode keeps the single-GPU negative law (one set per centre occurrence).
 Inputs are larger than L2 (tables 2 x 1.35 GB, CSR 0.8 GB, arc hash 4.3 GB), no L2 flush needed.
 """
 from __future__ import annotations
