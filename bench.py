@@ -480,6 +480,11 @@ def run_ours(a):
         roof_walk = {"kernel": ("walk_reject_indexed_kernel" if (a.walk_mode == "reject" and a.walk_indexed) else "walk_%s_kernel" % a.walk_mode), "bound": "hbm", "achieved": w_gbs, "peak": peak,
                      "unit": "GB/s", "frac": w_gbs / peak, "traffic": w_traffic, "traffic_source": w_traffic_src,
                      "frac_dram": (w_traffic / (walk_ms / a.steps / 1e3) / 1e9 / peak) if w_traffic else None,
+                     # against the random-access ceiling instead of the stream peak: a random 8-byte read costs HBM a
+                     # 128-byte access (4 sectors); the gather microbenchmark sustains 1.36e11-1.63e11 DRAM sectors/s
+                     # (profiles/r02_m_microbench_sectors.csv) -- 1.55e11 taken as the ceiling
+                     "frac_random_access": (w_traffic / 32.0 / (walk_ms / a.steps / 1e3) / 1.55e11) if w_traffic else None,
+                     "random_access_ceiling_dram_sectors_per_s": 1.55e11,
                      "algorithmic_bytes_per_launch": wbytes / a.steps,
                      "steps_per_s_kernel": S / (walk_ms / 1e3), "trials_per_step": (T / S) if S else None,
                      "probes_per_step": (P / S) if S else None, "ms_per_launch": walk_ms / a.steps}
