@@ -352,3 +352,21 @@ def test_reference_main_py_binds_to_the_dropins_without_a_gpu():
         sys.path.pop(0)
         for m in ("node2vec", "gensim", "gensim.models", "gensim.models.word2vec"):
             sys.modules.pop(m, None)
+
+
+def test_committed_ncu_traffic_matches_the_kernel_sources():
+    """profiles/ncu_traffic.json (what bench.py reports as roofline.traffic / frac_dram) was captured from
+    exactly the kernel sources in the tree: bench.py refuses a stale entry, this test makes it visible"""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        table = json.load(f)
+    assert {"sgns_train_kernel_v3", "sgns_train_kernel_v2", "sgns_group_kernel", "walk_reject_indexed_kernel"} <= set(table)
+    for kernel, ent in table.items():
+        assert ent["source_sha16"] == bench.source_sha16(kernel), "re-capture %s (scripts/capture_traffic.py)" % kernel
+        assert os.path.exists(os.path.join(ROOT, ent["profile"])), ent["profile"]
+        assert ent["dram_bytes_per_launch"] > 0
+    got, src = bench.ncu_traffic("sgns_train_kernel_v3", table["sgns_train_kernel_v3"]["workload"])
+    assert got == table["sgns_train_kernel_v3"]["dram_bytes_per_launch"] and src.startswith("profiles/")
+    assert bench.ncu_traffic("sgns_train_kernel_v3", "another workload")[0] is None
