@@ -139,6 +139,36 @@ def test_block_schedule_sequential_equals_oracle(n_parts, dim, neg_group, warps,
         assert np.isfinite(s0.cpu().numpy()).all() and float(s1.abs().max()) > 1e-3
 
 
+@pytest.mark.parametrize("n_parts", [1, 2])
+def test_wide_window_groups_beyond_one_tile(n_parts):
+    """window 20 on 80-step walks: a centre's group holds up to 40 contexts, more than the 24 that ride in
+    the header's 128-byte tile -- the rest are read from the stream directly; one warp == the oracle"""
+    from node2vec_by_ecc_b200 import BlockSgnsTrainer
+    z, g, corpus = corpus_from_golden("karate_p025_q4")
+    walks = corpus.walks[:120].contiguous()
+    n, L = walks.shape
+    counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=g.n)
+    tr = BlockSgnsTrainer(counts, dim=64, window=20, negative=5, sample=0.0, seed=4, local_parts=n_parts)
+    voc, id2index = oracle_vocab(tr, g.n)
+    tok, off = oracle_tokens(z["walks"][:n], id2index)
+    V = tr.V
+    rows = (V + n_parts - 1) // n_parts
+    parts0 = split_parts(oracle.sgns_init_syn0(V, 64, 4), n_parts, rows)
+    parts1 = [np.zeros((rows, 64), np.float32) for _ in range(n_parts)]
+    words, bounds = tr.make_groups(walks, None, n, L, 0, tr._params(0, 1, total_examples=n, sent_per_job=40), 0)
+    w = words.cpu().numpy().view(np.uint32)[: int(bounds[-1])]
+    widest = int((w[np.nonzero(w[:-2] & 0x80000000)[0] + 2] >> 16).max())
+    assert widest > 24 if n_parts == 1 else widest > 12
+    tr.train(walks, None, n, L, total_examples=n, sent_per_job=40, grid_warps=1)
+    pairs = oracle.sgns_block_pool(tok, off, voc, parts0, parts1, window=20, alpha=0.025, total_examples=n,
+                                   sent_per_job=40, seed=4, subsample=False)
+    tr.check_overflow()
+    assert int(tr.pairs[0]) == pairs
+    s0, s1 = tr.gather()
+    assert np.abs(s0.cpu().numpy() - join_parts(parts0, V)).max() < 2e-4
+    assert np.abs(s1.cpu().numpy() - join_parts(parts1, V)).max() < 2e-4
+
+
 def test_one_part_equals_the_sentence_major_kernel():
     """the block law does not depend on the partition: with one part (and one warp) the group kernel
     reproduces n2v_sgns_train's shared-negative run -- same draws, same order, same job alpha"""
