@@ -58,104 +58,188 @@ struct GroupsArgs {
     const uint32_t *cum_table; const int32_t *bucket_lo; int32_t neg_group;     // fill pass: the centres' negative sets
 };
 
-// One warp per sentence: sub-sample + window shrink exactly as the sentence-major kernels
-// (load_chunk), then every centre of this part emits one group per stream its window reaches.
+constexpr int BLK_STAGE_WORDS = 1024;    // per-warp staging of one batch of groups (fill pass)
+#ifndef N2V_GROUPS_MINB
+#define N2V_GROUPS_MINB 7                // the expansion is latency-bound: 7 blocks = 28 warps per SM (29 KB, <= 73 registers)
+#endif
+
+// One warp per sentence: sub-sample + window shrink exactly as the sentence-major kernels (load_chunk);
+// then ONE LANE PER CENTRE of this part, a batch of up to 32 centres at a time: every lane walks its own
+// window and counts its contexts per stream (8 x 8-bit fields), a warp scan of the per-stream group sizes
+// (16-bit fields) places every group, and the 5 negatives of all centres of the batch are drawn side by
+// side (Philox and table search spread over the lanes). The fill pass assembles the batch's groups in
+// shared memory, stream by stream, and copies each stream's run out with coalesced stores. The order
+// inside a stream is (sentence, centre position, context position), the same whatever the batching.
 template <bool FILL>
-__global__ void __launch_bounds__(SGNS_BLOCK)
+__global__ void __launch_bounds__(SGNS_BLOCK, N2V_GROUPS_MINB)
 sgns_groups_kernel(GroupsArgs g)
 {
-    __shared__ int32_t s_idx[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
-    __shared__ uint16_t s_pos[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
-    __shared__ uint8_t s_rw[SGNS_BLOCK / 32][SGNS_SMEM_TOKENS];
-    __shared__ long long s_cur[SGNS_BLOCK / 32][BLK_MAX_PARTS];      // next free word of every stream
-    __shared__ long long s_hdr[SGNS_BLOCK / 32][BLK_MAX_PARTS];      // header of the current centre's group (-1: none yet)
-    __shared__ int32_t s_cnt[SGNS_BLOCK / 32][BLK_MAX_PARTS];
-    __shared__ int32_t s_neg[SGNS_BLOCK / 32][BLK_FN];
+    constexpr int WPB = SGNS_BLOCK / 32;
+    constexpr uint32_t FULLM = 0xFFFFFFFFu;
+    static_assert(SGNS_SMEM_TOKENS <= 256 && BLK_STAGE_WORDS + GROUP_HDR < 65536, "s_list holds 8-bit positions, s_off 16-bit slots");
+    __shared__ int32_t s_idx[WPB][SGNS_SMEM_TOKENS];
+    __shared__ uint16_t s_pos[WPB][SGNS_SMEM_TOKENS];
+    __shared__ uint8_t s_rw[WPB][SGNS_SMEM_TOKENS];
+    __shared__ uint8_t s_list[WPB][SGNS_SMEM_TOKENS];                            // the chunk's centres of this part
+    __shared__ uint32_t s_stage[FILL ? WPB : 1][FILL ? BLK_STAGE_WORDS : 1];
+    __shared__ uint16_t s_off[FILL ? WPB : 1][BLK_MAX_PARTS][FILL ? 32 : 1];     // [stream][lane]: next context slot
+    __shared__ uint32_t s_neg[FILL ? WPB : 1][FILL ? 32 * BLK_FN : 1];           // [centre of the batch][negative]
     const SgnsArgs &a = g.a;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const WarpSentence ws{s_idx[wib], s_pos[wib], s_rw[wib]};
+    uint8_t *const list = s_list[wib];
+    uint32_t *const stage = s_stage[FILL ? wib : 0];
+    uint32_t *const neg = s_neg[FILL ? wib : 0];
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int32_t window = a.p.window, mask = g.n_parts - 1;
+    const int32_t window = a.p.window, n_parts = g.n_parts, mask = n_parts - 1;
     const uint32_t k0 = (uint32_t)a.p.seed, k1 = (uint32_t)(a.p.seed >> 32);
     const uint32_t ep8 = a.p.epoch << 8;
     const uint32_t lt = (1u << lane) - 1u;
+    int32_t batch = 32;
+    if (FILL) { const int32_t most = BLK_STAGE_WORDS / (2 * window + GROUP_HDR * n_parts); if (most < batch) batch = most; }
+    bool overflowed = false;
 
     for (int64_t s = warp; s < a.n_sent; s += n_warps) {
         const int64_t tb = a.sent_off ? a.sent_off[s] : s * (int64_t)a.stride;
         int64_t tl = a.sent_off ? a.sent_off[s + 1] - tb : (int64_t)a.stride;
         if (tl > a.p.max_sentence_len) tl = a.p.max_sentence_len;
         const uint64_t gs = (uint64_t)(a.sent_id_base + s);
-        if (lane < BLK_MAX_PARTS)
-            s_cur[wib][lane] = (FILL && lane < g.n_parts) ? (long long)g.offsets[(int64_t)lane * a.n_sent + s] : 0ll;
-        __syncwarp();
+        // lane b < n_parts keeps stream b's state: where this sentence's words start, words emitted so far
+        long long base = 0; uint32_t cur = 0;
+        if (FILL && lane < n_parts) base = (long long)g.offsets[(int64_t)lane * a.n_sent + s];
         int64_t t_next = 0;
         int32_t n_kept = 0, c_lo = 0, c_hi = 0;
         bool first_chunk = true;
         while (next_chunk(a, ws, tb, tl, t_next, gs, ep8, k0, k1, lane, n_kept, c_lo, c_hi, first_chunk)) {
-            // the centres of this part, in order: 32 candidates per ballot, then only the set bits
+            int32_t n_mine = 0;
             for (int32_t i0 = c_lo; i0 < c_hi; i0 += 32) {
-              uint32_t todo = __ballot_sync(0xFFFFFFFFu, i0 + lane < c_hi && (ws.idx[i0 + lane] & mask) == g.part);
-              while (todo) {
-                const int32_t i = i0 + __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int32_t centre = ws.idx[i];
-                int32_t j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
-                int32_t kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
-                if (lane < BLK_MAX_PARTS) { s_hdr[wib][lane] = -1ll; s_cnt[wib][lane] = 0; }
-                if (FILL && lane < BLK_FN) {
-                    // lane n draws negative n of this centre: the sentence-major kernel's draw_centre (Philox ctr
-                    // (gs lo, gs hi, position key << 16 | 0xFFFF, epoch << 8 | 1 + n / 4)) -> count^0.75 table -> the
-                    // word of the same local row in this part; position key = position / neg_group
-                    const uint32_t poskey = g.neg_group > 1 ? (uint32_t)ws.pos[i] / (uint32_t)g.neg_group : (uint32_t)ws.pos[i];
-                    const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (poskey << 16) | 0xFFFFu,
-                                                    ep8 | (uint32_t)(1 + (lane >> 2)), k0, k1);
-                    const uint32_t rr = (lane & 3) == 0 ? r.x : (lane & 3) == 1 ? r.y : (lane & 3) == 2 ? r.z : r.w;
-                    int32_t t = draw_negative(rr, g.cum_table, g.bucket_lo, a.p.V, a.p.bucket_bits) >> g.lg;
-                    if ((((int64_t)t << g.lg) | g.part) >= a.p.V) --t;
-                    s_neg[wib][lane] = t;
+                const bool mine = i0 + lane < c_hi && (ws.idx[i0 + lane] & mask) == g.part;
+                const uint32_t m = __ballot_sync(FULLM, mine);
+                if (mine) list[n_mine + __popc(m & lt)] = (uint8_t)(i0 + lane);
+                n_mine += __popc(m);
+            }
+            __syncwarp();
+            for (int32_t c0 = 0; c0 < n_mine; c0 += batch) {
+                const int32_t nb = n_mine - c0 < batch ? n_mine - c0 : batch;
+                const bool have = lane < nb;
+                const int32_t i = have ? (int32_t)list[c0 + lane] : 0;
+                int32_t j0 = 0, kend = 0;
+                if (have) {
+                    j0 = i - window + ws.rw[i]; if (j0 < 0) j0 = 0;
+                    kend = i + window + 1 - ws.rw[i]; if (kend > n_kept) kend = n_kept;
                 }
-                __syncwarp();
-                for (int32_t jb = j0; jb < kend; jb += 32) {
-                    const int32_t j = jb + lane;
-                    const bool valid = j < kend && j != i;
-                    const int32_t x = valid ? ws.idx[j] : 0;
-                    const int32_t b = valid ? (x & mask) : (BLK_MAX_PARTS + lane);
-                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
-                    const int rank = __popc(peers & lt);
-                    long long base = 0; bool fresh = false;
-                    if (valid) { base = s_cur[wib][b]; fresh = s_hdr[wib][b] < 0; }
-                    __syncwarp();
-                    if (valid && rank == 0) {
-                        if (fresh) s_hdr[wib][b] = base;
-                        s_cur[wib][b] = base + (fresh ? GROUP_HDR : 0) + __popc(peers);
-                        s_cnt[wib][b] += __popc(peers);
-                    }
-                    __syncwarp();
-                    if (FILL && valid) {
-                        const long long o = base + (fresh ? GROUP_HDR : 0) + rank;
-                        if (o < g.capacity) g.words[o] = (uint32_t)(x >> g.lg);
-                        else if (rank == 0) atomicAdd(g.overflow, 1ull);
-                    }
+                // contexts per stream: 8-bit fields (a window holds <= 2 * 96 of them), streams 0-3 | 4-7
+                uint32_t cl = 0, ch = 0;
+                for (int32_t j = j0; j < kend; ++j) {
+                    if (j == i) continue;
+                    const int32_t b = ws.idx[j] & mask;
+                    if (b < 4) cl += 1u << (8 * b); else ch += 1u << (8 * (b - 4));
                 }
-                if (FILL && lane < g.n_parts && s_hdr[wib][lane] >= 0) {
-                    const long long h = s_hdr[wib][lane];
-                    if (h + GROUP_HDR - 1 < g.capacity) {
-                        g.words[h] = GROUP_FLAG | (uint32_t)(centre >> g.lg);
-                        g.words[h + 1] = (uint32_t)s;
-                        g.words[h + 2] = (uint32_t)ws.pos[i] | ((uint32_t)s_cnt[wib][lane] << 16);
+                // group sizes in words, 16-bit fields, two streams per register; inclusive scan over the batch
+                // (32 groups of <= 200 words: no field overflows, and inc >= w field by field)
+                uint32_t w[4], inc[4];
 #pragma unroll
-                        for (int d = 0; d < BLK_FN; ++d) g.words[h + 3 + d] = (uint32_t)s_neg[wib][d];
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t c = q < 2 ? cl >> (16 * q) : ch >> (16 * (q - 2));
+                    const uint32_t c_even = c & 0xFFu, c_odd = (c >> 8) & 0xFFu;
+                    w[q] = (c_even ? c_even + GROUP_HDR : 0u) | ((c_odd ? c_odd + GROUP_HDR : 0u) << 16);
+                    inc[q] = w[q];
                 }
-                __syncwarp();
-              }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (2 * q < n_parts) {
+                            const uint32_t t = __shfl_up_sync(FULLM, inc[q], d);
+                            if (lane >= d) inc[q] += t;
+                        }
+                }
+                // lane b: words the batch adds to stream b
+                uint32_t tot = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (2 * q < n_parts) {
+                        const uint32_t t = __shfl_sync(FULLM, inc[q], 31);
+                        if ((lane >> 1) == q) tot = (lane & 1) ? t >> 16 : t & 0xFFFFu;
+                    }
+                if (lane >= n_parts) tot = 0;
+                if (FILL) {
+                    // negatives of the batch: Philox counters (gs lo, gs hi, position key << 16 | 0xFFFF, epoch << 8 |
+                    // 1 + n / 4) as the sentence-major kernel's draw_centre, two blocks per centre (negatives 0-3, 4)
+                    for (int32_t t = lane; t < 2 * nb; t += 32) {
+                        const int32_t slot = t >> 1, which = t & 1;
+                        const uint32_t pp = (uint32_t)ws.pos[list[c0 + slot]];
+                        const uint32_t poskey = g.neg_group > 1 ? pp / (uint32_t)g.neg_group : pp;
+                        const Philox4 r = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), (poskey << 16) | 0xFFFFu,
+                                                        ep8 | (uint32_t)(1 + which), k0, k1);
+                        uint32_t *o = neg + slot * BLK_FN;
+                        if (which == 0) { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; } else o[4] = r.x;
+                    }
+                    __syncwarp();
+                    // -> count^0.75 table -> the word of the same local row in this part
+                    for (int32_t t = lane; t < BLK_FN * nb; t += 32) {
+                        int32_t x = draw_negative(neg[t], g.cum_table, g.bucket_lo, a.p.V, a.p.bucket_bits) >> g.lg;
+                        if ((((int64_t)x << g.lg) | g.part) >= a.p.V) --x;
+                        neg[t] = (uint32_t)x;
+                    }
+                    // where stream b's run of this batch starts in the staging buffer
+                    uint32_t run = tot;
+#pragma unroll
+                    for (int d = 1; d < BLK_MAX_PARTS; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULLM, run, d);
+                        if (lane >= d) run += t;
+                    }
+                    run -= tot;
+                    __syncwarp();
+                    // headers, and every lane's first context slot per stream
+                    const uint32_t centre_row = have ? (uint32_t)(ws.idx[i] >> g.lg) : 0u;
+                    const uint32_t pos_i = have ? (uint32_t)ws.pos[i] : 0u;
+#pragma unroll
+                    for (int b = 0; b < BLK_MAX_PARTS; ++b)
+                        if (b < n_parts) {
+                            const uint32_t so = __shfl_sync(FULLM, run, b);
+                            const uint32_t cb = ((b < 4 ? cl : ch) >> (8 * (b & 3))) & 0xFFu;
+                            const uint32_t ex = ((inc[b >> 1] - w[b >> 1]) >> (16 * (b & 1))) & 0xFFFFu;
+                            if (have && cb) {
+                                uint32_t *h = stage + so + ex;
+                                h[0] = GROUP_FLAG | centre_row;
+                                h[1] = (uint32_t)s;
+                                h[2] = pos_i | (cb << 16);
+#pragma unroll
+                                for (int d = 0; d < BLK_FN; ++d) h[3 + d] = neg[lane * BLK_FN + d];
+                                s_off[wib][b][lane] = (uint16_t)(so + ex + GROUP_HDR);
+                            }
+                        }
+                    for (int32_t j = j0; j < kend; ++j) {
+                        if (j == i) continue;
+                        const int32_t x = ws.idx[j];
+                        const uint32_t p = s_off[wib][x & mask][lane];
+                        s_off[wib][x & mask][lane] = (uint16_t)(p + 1);
+                        stage[p] = (uint32_t)(x >> g.lg);
+                    }
+                    __syncwarp();
+                    // copy every stream's run out
+                    for (int b = 0; b < n_parts; ++b) {
+                        const uint32_t n_w = __shfl_sync(FULLM, tot, b), so = __shfl_sync(FULLM, run, b);
+                        const long long go = __shfl_sync(FULLM, base + (long long)cur, b);
+                        const long long room = g.capacity - go;
+                        const uint32_t fit = room >= (long long)n_w ? n_w : room > 0 ? (uint32_t)room : 0u;
+                        if (fit < n_w) overflowed = true;
+                        uint32_t *const out = g.words + go;
+                        const uint32_t *const in = stage + so;
+                        for (uint32_t k = lane; k < fit; k += 32) out[k] = in[k];
+                    }
+                    __syncwarp();
+                }
+                cur += tot;
             }
             __syncwarp();
         }
-        if (!FILL && lane < g.n_parts) g.counts[(int64_t)lane * a.n_sent + s] = (int32_t)s_cur[wib][lane];
+        if (!FILL && lane < n_parts) g.counts[(int64_t)lane * a.n_sent + s] = (int32_t)cur;
         __syncwarp();
     }
+    if (FILL && overflowed) atomicAdd(g.overflow, 1ull);
 }
 
 struct TrainGroupsArgs {

@@ -205,6 +205,34 @@ def test_device_side_bounds_equal_host_bounds():
     assert torch.equal(res[0][1][0], res[1][1][0]) and torch.equal(res[0][1][1], res[1][1][1])
 
 
+def test_a_pool_that_does_not_fit_is_reported_and_clamped():
+    """fill with half the room: nothing is written past the capacity, what fits is unchanged, the
+    overflow counter is raised and check_overflow() raises"""
+    import ctypes as C
+    from node2vec_by_ecc_b200 import N2VError
+    from node2vec_by_ecc_b200._lib import check, lib, ptr, stream
+    z, g, corpus = corpus_from_golden("karate_p025_q4")
+    walks = corpus.walks
+    n, L = walks.shape
+    tr = make_trainer(walks, g.n, 4)
+    P = tr._params(0, 1, total_examples=n, sent_per_job=25)
+    words, bounds = tr.make_groups(walks, None, n, L, 0, P, 1)
+    total = bounds[-1]
+    full = words[:total].clone()
+    cap = total // 2
+    buf = torch.full((total,), 0x7FFFFFFF, dtype=torch.int32, device=walks.device)
+    b = tr._buf[1]
+    check(lib().n2v_sgns_groups_fill(ptr(walks), None, C.c_int64(n), C.c_int32(L), C.c_int64(0), ptr(tr.vocab_of_id),
+                                     ptr(tr.keep_thr), C.byref(P), C.c_int32(1), C.c_int32(4), ptr(tr.cum_table),
+                                     ptr(tr.bucket_lo), C.c_int32(1), ptr(b["offsets"]), ptr(buf), C.c_int64(cap),
+                                     ptr(b["overflow"]), stream()))
+    assert bool((buf[cap:] == 0x7FFFFFFF).all())
+    assert torch.equal(buf[:bounds[1]], full[:bounds[1]])           # stream 0 lies below the capacity
+    assert int(b["overflow"].item()) > 0
+    with pytest.raises(N2VError):
+        tr.check_overflow()
+
+
 def test_block_wide_close_to_sequential():
     """full Hogwild width: same pairs, embeddings close to the one-warp run (Hogwild noise only)"""
     z, g, corpus = corpus_from_golden("karate_p025_q4")
