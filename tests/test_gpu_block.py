@@ -79,8 +79,12 @@ def test_group_streams_equal_oracle(n_parts):
     assert int(ref.pairs[0]) == pairs
 
 
-def test_group_streams_ragged_long_sentences():
-    """sent_off corpus with sentences longer than the staging buffer (streamed in chunks)"""
+@pytest.mark.parametrize("n_parts,window,neg_group", [(4, 10, 1), (8, 40, 1), (2, 96, 1), (1, 96, 3), (8, 1, 1)])
+def test_group_streams_ragged_long_sentences(n_parts, window, neg_group):
+    """sent_off corpus with sentences longer than the staging buffer (streamed in chunks); wide windows
+    make the batches of centres small (4 centres at window 96: many batches per chunk, groups of up to
+    192 pairs), window 1 makes them full"""
+    from node2vec_by_ecc_b200 import BlockSgnsTrainer
     rng = np.random.default_rng(5)
     n_ids, lens = 300, rng.integers(0, 900, size=40)
     lens[3] = 0
@@ -88,17 +92,22 @@ def test_group_streams_ragged_long_sentences():
     tok_ids = rng.integers(0, n_ids, size=int(off[-1])).astype(np.int32)
     tok_ids[rng.random(tok_ids.shape[0]) < 0.02] = -1
     walks = torch.as_tensor(tok_ids).cuda()
-    tr = make_trainer(walks, n_ids, 4, dim=32)
+    counts = torch.bincount(walks[walks >= 0].to(torch.int64), minlength=n_ids)
+    tr = BlockSgnsTrainer(counts, dim=32, window=window, negative=5, sample=1e-3, seed=4, local_parts=n_parts,
+                          neg_group=neg_group)
     voc, id2index = oracle_vocab(tr, n_ids)
     tok = np.where(tok_ids >= 0, id2index[np.maximum(tok_ids, 0)], -1).astype(np.int32)
     P = tr._params(2, 1)
     off_d = torch.as_tensor(off).cuda()
-    for k in range(4):
+    for k in range(n_parts):
         words, bounds = tr.make_groups(walks, off_d, len(lens), 0, 7, P, k)
-        want = oracle.sgns_make_groups(tok, off, voc, k, 4, window=10, seed=4, epoch=2, sent_id_base=7)
+        want = oracle.sgns_make_groups(tok, off, voc, k, n_parts, window=window, seed=4, epoch=2, sent_id_base=7,
+                                       neg_group=neg_group)
         got = words.cpu().numpy().view(np.uint32)
-        for b in range(4):
+        for b in range(n_parts):
+            assert bounds[b + 1] - bounds[b] == len(want[b])
             assert np.array_equal(got[bounds[b]:bounds[b + 1]], want[b])
+    tr.check_overflow()
 
 
 @pytest.mark.parametrize("n_parts,dim,neg_group,warps,hot", [(1, 128, 1, 1, 0), (2, 128, 1, 1, 0), (4, 64, 1, 1, 0), (8, 128, 1, 1, 0),
